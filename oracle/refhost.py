@@ -26,52 +26,70 @@ def available():
     return all(os.path.exists(os.path.join(REF_DIR, "libjuicy_ref_%s.so" % p)) for p in PLUGINS)
 
 
+class _Api:
+    """Resolves <prefix>_<name> symbols of one oracle library."""
+
+    def __init__(self, lib, prefix):
+        self._lib, self._prefix = lib, prefix
+
+    def __getattr__(self, name):
+        return getattr(self._lib, "%s_%s" % (self._prefix, name))
+
+
+def bind(path, prefix, create_argtypes):
+    """Load an oracle library and declare the harness signatures (shared by oracle.port)."""
+    raw = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
+    lib = _Api(raw, prefix)
+    lib.create.restype = ctypes.c_void_p
+    lib.create.argtypes = create_argtypes
+    lib.destroy.argtypes = [ctypes.c_void_p]
+    lib.prepare.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+    lib.num_params.argtypes = [ctypes.c_void_p]
+    lib.param_id.restype = ctypes.c_char_p
+    lib.param_id.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.param_range.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    lib.get_param.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float)]
+    lib.set_param.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_float]
+    lib.set_param_normalised.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_float]
+    lib.num_programs.argtypes = [ctypes.c_void_p]
+    lib.get_program.argtypes = [ctypes.c_void_p]
+    lib.set_program.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.program_name.restype = ctypes.c_char_p
+    lib.program_name.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.process.restype = ctypes.c_long
+    lib.process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p]
+    lib.latest.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.render_clips.restype = ctypes.c_double
+    lib.render_clips.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_long,
+                                         ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+    return lib
+
+
 def _lib(plugin):
     if plugin not in _libs:
         path = os.path.join(REF_DIR, "libjuicy_ref_%s.so" % plugin)
-        lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
-        lib.ref_create.restype = ctypes.c_void_p
-        lib.ref_create.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int]
-        lib.ref_destroy.argtypes = [ctypes.c_void_p]
-        lib.ref_prepare.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
-        lib.ref_num_params.argtypes = [ctypes.c_void_p]
-        lib.ref_param_id.restype = ctypes.c_char_p
-        lib.ref_param_id.argtypes = [ctypes.c_void_p, ctypes.c_int]
-        lib.ref_param_range.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
-        lib.ref_get_param.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float)]
-        lib.ref_set_param.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_float]
-        lib.ref_set_param_normalised.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_float]
-        lib.ref_num_programs.argtypes = [ctypes.c_void_p]
-        lib.ref_get_program.argtypes = [ctypes.c_void_p]
-        lib.ref_set_program.argtypes = [ctypes.c_void_p, ctypes.c_int]
-        lib.ref_program_name.restype = ctypes.c_char_p
-        lib.ref_program_name.argtypes = [ctypes.c_void_p, ctypes.c_int]
-        lib.ref_process.restype = ctypes.c_long
-        lib.ref_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_void_p]
-        lib.ref_latest.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-        lib.ref_render_clips.restype = ctypes.c_double
-        lib.ref_render_clips.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_long,
-                                         ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
-        _libs[plugin] = lib
+        _libs[plugin] = bind(path, "ref", [ctypes.c_int, ctypes.c_double, ctypes.c_int])
     return _libs[plugin]
 
 
-class RefPlugin:
-    """One instance of a reference plugin class behind the headless harness."""
+class OraclePlugin:
+    """Common driver over the ref_/jo_ harness interface (one plugin instance)."""
 
-    def __init__(self, plugin, channels=2, sample_rate=48000.0, block_size=512):
-        if plugin not in PLUGINS:
-            raise ValueError("unknown plugin %r" % (plugin,))
-        self.plugin = plugin
-        self.lib = _lib(plugin)
+    plugin = None
+    lib = None
+
+    def _init(self, lib, create_args, channels, sample_rate, block_size):
+        self.lib = lib
         self.channels = channels
         self.sample_rate = float(sample_rate)
         self.block_size = int(block_size)
-        self.h = ctypes.c_void_p(self.lib.ref_create(channels, self.sample_rate, self.block_size))
+        self.h = ctypes.c_void_p(self.lib.create(*create_args))
+        if not self.h:
+            raise RuntimeError("oracle create failed")
 
     def close(self):
         if self.h:
-            self.lib.ref_destroy(self.h)
+            self.lib.destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -82,41 +100,41 @@ class RefPlugin:
             self.sample_rate = float(sample_rate)
         if block_size is not None:
             self.block_size = int(block_size)
-        self.lib.ref_prepare(self.h, self.sample_rate, self.block_size)
+        self.lib.prepare(self.h, self.sample_rate, self.block_size)
 
     def param_ids(self):
-        return [self.lib.ref_param_id(self.h, i).decode() for i in range(self.lib.ref_num_params(self.h))]
+        return [self.lib.param_id(self.h, i).decode() for i in range(self.lib.num_params(self.h))]
 
     def param_range(self, index):
         out = (ctypes.c_float * 3)()
-        self.lib.ref_param_range(self.h, index, out)
+        self.lib.param_range(self.h, index, out)
         return tuple(out)
 
     def get_param(self, pid):
         v = ctypes.c_float()
-        if self.lib.ref_get_param(self.h, pid.encode(), ctypes.byref(v)) != 0:
+        if self.lib.get_param(self.h, pid.encode(), ctypes.byref(v)) != 0:
             raise KeyError(pid)
         return v.value
 
     def set_param(self, pid, plain):
-        if self.lib.ref_set_param(self.h, pid.encode(), float(plain)) != 0:
+        if self.lib.set_param(self.h, pid.encode(), float(plain)) != 0:
             raise KeyError(pid)
 
     def set_param_normalised(self, pid, n):
-        if self.lib.ref_set_param_normalised(self.h, pid.encode(), float(n)) != 0:
+        if self.lib.set_param_normalised(self.h, pid.encode(), float(n)) != 0:
             raise KeyError(pid)
 
     def params(self):
         return {p: self.get_param(p) for p in self.param_ids()}
 
     def num_programs(self):
-        return self.lib.ref_num_programs(self.h)
+        return self.lib.num_programs(self.h)
 
     def set_program(self, i):
-        self.lib.ref_set_program(self.h, int(i))
+        self.lib.set_program(self.h, int(i))
 
     def program_name(self, i):
-        return self.lib.ref_program_name(self.h, int(i)).decode()
+        return self.lib.program_name(self.h, int(i)).decode()
 
     def process(self, audio):
         """audio: float32 [channels][n] (C-contiguous). Returns (out, history[nblocks][16])."""
@@ -125,7 +143,7 @@ class RefPlugin:
         n = a.shape[1]
         nblocks = (n + self.block_size - 1) // self.block_size
         hist = np.zeros((max(nblocks, 1), 16), dtype=np.float32)
-        got = self.lib.ref_process(self.h, a.ctypes.data, n, self.block_size, hist.ctypes.data)
+        got = self.lib.process(self.h, a.ctypes.data, n, self.block_size, hist.ctypes.data)
         return a, hist[:got]
 
     def render_clips(self, clips):
@@ -134,19 +152,29 @@ class RefPlugin:
         a = np.ascontiguousarray(clips, dtype=np.float32).copy()
         assert a.ndim == 3 and a.shape[1] == self.channels
         rec = np.zeros((a.shape[0], 16), dtype=np.float32)
-        secs = self.lib.ref_render_clips(self.h, a.ctypes.data, a.shape[0], a.shape[2], self.block_size,
+        secs = self.lib.render_clips(self.h, a.ctypes.data, a.shape[0], a.shape[2], self.block_size,
                                          self.sample_rate, rec.ctypes.data)
         return a, rec, secs
 
 
-def run_chain(chain, audio, channels=2, sample_rate=48000.0, block_size=512, programs=None, params=None):
+class RefPlugin(OraclePlugin):
+    """One instance of a reference plugin class behind the headless harness."""
+
+    def __init__(self, plugin, channels=2, sample_rate=48000.0, block_size=512):
+        if plugin not in PLUGINS:
+            raise ValueError("unknown plugin %r" % (plugin,))
+        self.plugin = plugin
+        self._init(_lib(plugin), (channels, float(sample_rate), int(block_size)), channels, sample_rate, block_size)
+
+
+def run_chain(chain, audio, channels=2, sample_rate=48000.0, block_size=512, programs=None, params=None, cls=None):
     """Push one clip [channels][n] through `chain` (list of plugin names), plugin by plugin.
     Equivalent to the per-block chain because every plugin is causal and sees identical blocking.
     Returns (out, [history per plugin]).  programs: {slot: idx}; params: {slot: {id: plain}}."""
     x = np.ascontiguousarray(audio, dtype=np.float32)
     hists = []
     for slot, name in enumerate(chain):
-        p = RefPlugin(name, channels, sample_rate, block_size)
+        p = (cls or RefPlugin)(name, channels, sample_rate, block_size)
         if programs and slot in programs:
             p.set_program(programs[slot])
         if params and slot in params:
