@@ -1,0 +1,182 @@
+/* juicy_batch.h -- C ABI of the B200-native JuicySuite batch engine.
+ *
+ * One engine = N identical instances ("clips") of one plugin, or of a chain of
+ * plugins, rendered together on one GPU.  The entry points are what a binding
+ * of the reference's processor/parameter API would call; each cites the
+ * reference interface it replaces (paths relative to /root/reference).
+ * INTEGRATION.md shows the C++ and ctypes stubs a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns JB_OK (0) or a
+ *     negative jb_status and records a message readable via jb_last_error();
+ *   - audio is planar fp32, [clip][channel][sample], exactly N concatenated
+ *     juce::AudioBuffer<float> images; "device" pointers are CUDA device
+ *     pointers on the engine's GPU, "host" pointers are ordinary memory;
+ *   - `slot` is the position of a plugin inside the engine's chain (0-based);
+ *   - parameter values are the plain (de-normalised) floats that
+ *     `*parameters.getRawParameterValue(id)` yields in the reference.
+ *   - there is no CPU fallback: without a CUDA device every call that needs
+ *     one fails with JB_ERR_CUDA.
+ */
+#ifndef JUICY_BATCH_H
+#define JUICY_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JB_ABI_VERSION 1
+#define JB_MAX_CHAIN 8
+#define JB_ALL_CLIPS (-1)
+
+typedef enum jb_status {
+    JB_OK = 0,
+    JB_ERR_ARG = -1,       /* bad argument (null pointer, unknown id, size mismatch) */
+    JB_ERR_STATE = -2,     /* call order violated (e.g. process before prepare)      */
+    JB_ERR_CUDA = -3,      /* CUDA runtime / driver error, or no device               */
+    JB_ERR_UNSUPPORTED = -4
+} jb_status;
+
+/* Plugin kinds, in the order of CMakeLists.txt:63-69 (add_juicy_plugin calls). */
+typedef enum jb_plugin_kind {
+    JB_INFER = 0,     /* src/plugins/JuicyInfer     */
+    JB_PUNCH = 1,     /* src/plugins/JuicyPunch     */
+    JB_SATURATOR = 2, /* src/plugins/JuicySaturator */
+    JB_WIDTH = 3,     /* src/plugins/JuicyWidth     */
+    JB_COHERE = 4,    /* src/plugins/JuicyCohere    */
+    JB_TEXTURE = 5,   /* src/plugins/JuicyTexture   */
+    JB_MOTION = 6,    /* src/plugins/JuicyMotion    */
+    JB_NUM_KINDS = 7
+} jb_plugin_kind;
+
+/* Mirrors `struct JuicinessMetrics` (src/shared/JuicinessAnalyzer.h:6-21), field
+ * for field, followed by the plugin's output parameters as the host sees them:
+ * `juiciness` (every plugin, e.g. JuicyPunch/PluginProcessor.cpp:56-62,123) and
+ * `aux` = Cohere's `contextfit` (JuicyCohere/PluginProcessor.cpp:91-92), else 0.
+ * The values are what `getLatestMetrics()` returns after a processBlock, e.g.
+ * JuicyPunch/PluginProcessor.cpp:190-202; for Infer the five feature slots carry
+ * the triangle metrics (JuicyInfer/PluginProcessor.cpp:164-181). */
+typedef struct jb_metrics {
+    float score, preScore, postScore;
+    float emphasis, coherence, synesthesia, fatigueRisk, repetitionDensity;
+    float punch, richness, clarity, width, monoSafety;
+    float juiciness; /* de-normalised `juiciness` output parameter */
+    float aux;       /* `contextfit` for JB_COHERE, otherwise 0 */
+    float reserved;
+} jb_metrics;
+
+typedef struct jb_param_info {
+    const char* id;   /* APVTS parameter id */
+    const char* name;
+    float min_value, max_value, interval, default_value;
+    int is_output;    /* 1 for juiciness / contextfit / Infer's triangle outputs */
+} jb_param_info;
+
+typedef struct jb_engine jb_engine;
+
+const char* jb_last_error(void);
+int jb_abi_version(void);
+/* Number of CUDA devices visible (0 without a GPU; never an error). */
+int jb_device_count(void);
+
+/* createPluginFilter() x N (e.g. JuicySaturator/PluginProcessor.cpp:201-204) and the
+ * constructors' bus layout + setCurrentProgram(0) (:26-33).  `chain` holds
+ * chain_len jb_plugin_kind values applied in order to every clip; n_channels is
+ * the bus layout (isBusesLayoutSupported: mono or stereo in == out, e.g.
+ * JuicyPunch/PluginProcessor.cpp:48-54; this build renders stereo only). */
+int jb_create(const int* chain, int chain_len, int n_clips, int n_channels, int device, jb_engine** out);
+int jb_destroy(jb_engine* e);
+
+int jb_chain_length(const jb_engine* e);
+int jb_chain_kind(const jb_engine* e, int slot);
+int jb_num_clips(const jb_engine* e);
+
+/* AudioProcessor::prepareToPlay(sampleRate, samplesPerBlock) for every plugin of the
+ * chain (e.g. JuicyMotion/PluginProcessor.cpp:12-29): sets the rate, (re)allocates
+ * and clears all DSP + analyzer state.  jb_reset clears state again at the same
+ * rate (a second prepareToPlay). */
+int jb_prepare(jb_engine* e, double sample_rate, int samples_per_block);
+int jb_reset(jb_engine* e);
+
+/* Parameters: AudioProcessorValueTreeState "PARAMS" (ids, ranges, defaults of
+ * createParameterLayout(), e.g. JuicySaturator/PluginProcessor.cpp:189-199). */
+int jb_num_params(const jb_engine* e, int slot);
+int jb_param_info_at(const jb_engine* e, int slot, int index, jb_param_info* out);
+/* `*parameters.getRawParameterValue(id)` */
+int jb_get_param(const jb_engine* e, int slot, const char* id, float* out);
+/* host automation to a plain value: param->setValueNotifyingHost(range.convertTo0to1(v)) */
+int jb_set_param(jb_engine* e, int slot, const char* id, float plain_value);
+/* param->setValueNotifyingHost(normalised) */
+int jb_set_param_normalised(jb_engine* e, int slot, const char* id, float normalised);
+
+/* Programs: getNumPrograms / getCurrentProgram / setCurrentProgram / getProgramName
+ * (e.g. JuicyWidth/PluginProcessor.cpp:171-210). */
+int jb_num_programs(const jb_engine* e, int slot);
+int jb_get_program(const jb_engine* e, int slot);
+int jb_set_program(jb_engine* e, int slot, int index);
+const char* jb_program_name(const jb_engine* e, int slot, int index);
+
+/* processBlock(AudioBuffer<float>&, MidiBuffer&) for every block of every clip and
+ * every plugin of the chain (e.g. JuicyPunch/PluginProcessor.cpp:64-124): walks
+ * n_samples in blocks of samples_per_block (ragged last block), carrying state
+ * across calls like consecutive host callbacks.  d_in/d_out: device pointers,
+ * [n_clips][n_channels][n_samples] fp32; d_out may equal d_in (in place).
+ * Asynchronous on the engine's stream. */
+int jb_process(jb_engine* e, const float* d_in, float* d_out, int n_samples);
+/* Same through HOST buffers: uploads, renders and downloads clip ranges in a
+ * pipelined fashion (copies overlapped with kernels); returns when h_out is
+ * complete.  h_out may equal h_in. */
+int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples);
+int jb_synchronize(jb_engine* e);
+/* Run on a caller-owned cudaStream_t (e.g. the framework's current stream). */
+int jb_set_stream(jb_engine* e, void* cuda_stream);
+
+/* getLatestMetrics() of every clip after the most recent block (host buffer,
+ * n_clips records).  Synchronises the engine's stream. */
+int jb_get_metrics(jb_engine* e, int slot, jb_metrics* out);
+/* Device-resident copy, structure-of-arrays [16][n_clips] floats in jb_metrics field
+ * order (for gathering scores across GPUs without a host round trip). */
+int jb_metrics_device(jb_engine* e, int slot, const float** d_out);
+
+/* Optional per-block history (what host automation of `juiciness` sees over a
+ * render): keep the record of every block for up to max_blocks blocks since the
+ * last prepare/reset.  out: [n_blocks][n_clips] records. */
+int jb_enable_history(jb_engine* e, int max_blocks);
+int jb_history_blocks(const jb_engine* e);
+int jb_get_history(jb_engine* e, int slot, int first_block, int n_blocks, jb_metrics* out);
+
+/* Seeded synthetic clips written straight into device memory:
+ * kind 0 sweep, 1 noise, 2 impulse train, 3 drum hit, 4 mixed (clip mod 4).
+ * first_clip offsets the per-clip seeds so shards of one job stay distinct. */
+int jb_synth_fill(float* d_audio, int kind, long long first_clip, int n_clips, int n_channels,
+                  int n_samples, double sample_rate, unsigned int seed, int device, void* cuda_stream);
+
+/* The same clips generated on the host (plain C++; needs no GPU): the parity tests feed
+ * these to both the engine and the CPU oracle.  The device generator uses the GPU's
+ * own sinf/expf, so its samples agree with these to rounding, not bit for bit. */
+int jb_synth_fill_host(float* h_audio, int kind, long long first_clip, int n_clips, int n_channels,
+                       int n_samples, double sample_rate, unsigned int seed);
+
+/* Number of kernel launches issued by this library since load (bench evidence). */
+long long jb_launch_count(void);
+/* Device time spent in the render kernel since the previous call of this function:
+ * the sum over launches of (stop - start) CUDA events recorded on the engine's stream
+ * around every launch, and the number of launches summed.  Synchronises the stream. */
+int jb_kernel_time_ms(jb_engine* e, double* ms, long long* launches);
+
+/* Plumbing for callers without a CUDA runtime of their own (the ctypes tests, the C++
+ * demo): page-locked host memory and raw device memory on `device`. */
+int jb_host_alloc(size_t bytes, void** out);
+int jb_host_free(void* p);
+int jb_device_alloc(int device, size_t bytes, void** out);
+int jb_device_free(int device, void* p);
+int jb_copy_to_device(int device, void* d_dst, const void* h_src, size_t bytes);
+int jb_copy_to_host(int device, void* h_dst, const void* d_src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JUICY_BATCH_H */

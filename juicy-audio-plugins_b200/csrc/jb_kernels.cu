@@ -1,0 +1,1125 @@
+// jb_kernels.cu -- sm_100a device code of the JuicySuite batch engine.
+//
+// Mapping: one lane = one clip (stereo pair); a warp walks 32
+// clips through time.  Per 512-sample block the lane makes chainLen+1 "sweeps":
+//
+//   sweep 0      : pre-analysis of plugin 0 on the block's input
+//   sweep s+1    : DSP of plugin s  ->  post-analysis of plugin s  +  pre-analysis
+//                  (and block pre-pass) of plugin s+1 on the samples just produced
+//
+// which reproduces the reference's per-plugin processBlock order
+// analyze(in) -> DSP -> analyze(out) with ONE shared analyzer per plugin
+// (e.g. JuicyPunch/PluginProcessor.cpp:82,114) while reading
+// and writing every sample once per sweep.  All recurrences keep the
+// reference's fp32 operand order; this file is compiled with
+// -fmad=false -ftz=true -prec-div=true -prec-sqrt=true (see Makefile).
+//
+// Reference lines are cited per routine, relative to /root/reference.
+#include "jb_kernels.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#define PI_F 3.14159265358979323846f
+#define TWO_PI_F 6.28318530717958647692f
+
+namespace {
+
+enum { K_INFER = 0, K_PUNCH = 1, K_SAT = 2, K_WIDTH = 3, K_COHERE = 4, K_TEXTURE = 5, K_MOTION = 6 };
+
+// juce::jmax / jmin / jlimit / jmap as comparisons
+__device__ __forceinline__ float jmaxf(float a, float b) { return a < b ? b : a; }
+__device__ __forceinline__ float jminf(float a, float b) { return b < a ? b : a; }
+__device__ __forceinline__ float jlimitf(float lo, float hi, float v) { return v < lo ? lo : (hi < v ? hi : v); }
+__device__ __forceinline__ float jmap3(float v, float lo, float hi) { return lo + v * (hi - lo); }
+
+// Per-sample transcendentals.  The oracle uses glibc's (nearly correctly rounded)
+// float functions; evaluating in fp64 and rounding once keeps the device within
+// a fraction of an ulp of them where the recurrence is sensitive (Texture-metal
+// cos); the others use CUDA's <=2 ulp float versions.
+__device__ __forceinline__ float cos_exact(float x) { return (float) cos((double) x); }
+__device__ __forceinline__ float pow_exact(float x, float y) { return (float) pow((double) x, (double) y); }
+__device__ __forceinline__ float log10_exact(float x) { return (float) log10((double) x); }
+
+struct Lane {
+    const ProcArgs& a;
+    long long clip;
+    __device__ __forceinline__ float* sp(int var) const { return a.state + (long long) var * a.clipPitch + clip; }
+    __device__ __forceinline__ float ld(int var) const { return *sp(var); }
+    __device__ __forceinline__ void st(int var, float v) const { *sp(var) = v; }
+    __device__ __forceinline__ int ldi(int var) const { return __float_as_int(*sp(var)); }
+    __device__ __forceinline__ void sti(int var, int v) const { *sp(var) = __int_as_float(v); }
+};
+
+// ------------------------------------------------------------------ analyzer
+// JuicinessAnalyzer::analyze, src/shared/JuicinessAnalyzer.cpp:31-155.
+
+// Sums that depend only on the block's samples (not on analyzer state), shared by
+// the post-analysis of plugin s and the pre-analysis of plugin s+1 (:76-77, :86-91,
+// and getRMSLevel :105-106, which accumulates in double).
+struct BlockStats {
+    float rms = 0.0f, peak = 0.0f, side = 0.0f, corr = 0.0f;
+    double l2 = 0.0, r2 = 0.0;
+    __device__ __forceinline__ void step(float l, float r, float mono)
+    {
+        rms += mono * mono;                 // rmsAccum; midAccum is the same expression (:62, :86, :88)
+        peak = jmaxf(peak, fabsf(mono));
+        const float s = 0.5f * (l - r);
+        side += s * s;
+        corr += l * r;
+        const double dl = (double) l, dr = (double) r;
+        l2 = fma(dl, dl, l2);               // dl*dl is exact in fp64, so the fused form rounds identically
+        r2 = fma(dr, dr, r2);
+    }
+};
+
+struct Metrics {
+    float score, emphasis, coherence, synesthesia, fatigueRisk, repetitionDensity, punch, richness, clarity, width, monoSafety;
+};
+
+// The state-dependent walk: two attack/release envelopes, onset state machine,
+// two one-pole band splits (:64-75, :79-84).
+struct AnaWalk {
+    float sEnv, lEnv, low, high;
+    int cool;
+    float trAcc = 0.0f, lowAcc = 0.0f, highAcc = 0.0f;
+    int onsets = 0;
+
+    __device__ __forceinline__ void load(const Lane& L, int base)
+    {
+        sEnv = L.ld(base + AV_SHORT);
+        lEnv = L.ld(base + AV_LONG);
+        low = L.ld(base + AV_LOW);
+        high = L.ld(base + AV_HIGH);
+        cool = L.ldi(base + AV_COOLDOWN);
+    }
+    __device__ __forceinline__ void step(float mono, const AnaCoef& c)
+    {
+        const float a = fabsf(mono);
+        {   // updateEnvelope (:24-29)
+            const bool up = a > sEnv;
+            sEnv = (up ? c.omaS : c.omrS) * a + (up ? c.aS : c.rS) * sEnv;
+        }
+        {
+            const bool up = a > lEnv;
+            lEnv = (up ? c.omaL : c.omrL) * a + (up ? c.aL : c.rL) * lEnv;
+        }
+        const float tr = jmaxf(0.0f, sEnv - lEnv);
+        trAcc += tr;
+        if (cool > 0)
+            --cool;
+        if (tr > 0.045f && cool <= 0) {
+            ++onsets;
+            cool = c.cooldownLen;
+        }
+        low += c.lowCoeff * (mono - low);
+        high += c.highCoeff * (mono - high);
+        const float hi = mono - high;
+        lowAcc += low * low;
+        highAcc += hi * hi;
+    }
+    // Feature mapping and blend (:94-141); updates the two per-call EMAs and stores the state.
+    __device__ Metrics finish(const Lane& L, int base, const BlockStats& s, int n, const AnaCoef& c)
+    {
+        const float invN = 1.0f / (float) n;
+        const float rms = sqrtf(s.rms * invN + 1.0e-12f);
+        const float crest = s.peak / (rms + 1.0e-6f);
+        const float lowEnergy = lowAcc * invN;
+        const float highEnergy = highAcc * invN;
+        const float lowHighRatio = lowEnergy / (highEnergy + 1.0e-8f);
+        const float widthRatio = s.side / (s.rms + s.side + 1.0e-8f);
+
+        const float lEnergy = (float) sqrt(s.l2 / (double) n);
+        const float rEnergy = (float) sqrt(s.r2 / (double) n);
+        float corr = s.corr * invN / (lEnergy * rEnergy + 1.0e-6f);
+        corr = jlimitf(-1.0f, 1.0f, corr);
+
+        Metrics m;
+        m.punch = jlimitf(0.0f, 1.0f, 6.0f * trAcc * invN / (rms + 1.0e-5f));
+        m.richness = jlimitf(0.0f, 1.0f, (2.3f - crest) * 0.65f + (rms * 2.0f));
+        float clarity = 1.0f;
+        if (lowHighRatio > 2.5f)
+            clarity -= jlimitf(0.0f, 0.6f, (lowHighRatio - 2.5f) * 0.15f);
+        if (highEnergy > 0.03f)
+            clarity -= jlimitf(0.0f, 0.5f, (highEnergy - 0.03f) * 8.0f);
+        m.clarity = jlimitf(0.0f, 1.0f, clarity);
+        m.width = jlimitf(0.0f, 1.0f, widthRatio * 2.0f);
+        m.monoSafety = jlimitf(0.0f, 1.0f, 0.5f * (corr + 1.0f));
+
+        const float blockSeconds = (float) n / c.srf;
+        const float onsetRate = blockSeconds > 0.0f ? (float) onsets / blockSeconds : 0.0f;
+        float repEma = L.ld(base + AV_REP_EMA);
+        repEma += (onsetRate - repEma) * 0.08f;
+        m.repetitionDensity = jlimitf(0.0f, 1.0f, repEma / 12.0f);
+
+        m.emphasis = jlimitf(0.0f, 1.0f, 0.62f * m.punch + 0.38f * jlimitf(0.0f, 1.0f, trAcc * invN * 8.5f));
+        m.coherence = jlimitf(0.0f, 1.0f, 0.50f * m.clarity + 0.30f * m.monoSafety + 0.20f * (1.0f - fabsf(m.width - 0.45f)));
+        m.synesthesia = jlimitf(0.0f, 1.0f, 0.45f * m.richness + 0.30f * jlimitf(0.0f, 1.0f, lowHighRatio / 3.5f)
+                                                + 0.25f * jlimitf(0.0f, 1.0f, trAcc * invN * 5.0f));
+        const float crestPenalty = jlimitf(0.0f, 1.0f, (1.8f - crest) * 1.1f);
+        const float harshPenalty = jlimitf(0.0f, 1.0f, highEnergy * 12.0f);
+        const float instantFatigue = jlimitf(0.0f, 1.0f, 0.35f * crestPenalty + 0.35f * harshPenalty + 0.30f * m.repetitionDensity);
+        float fatEma = L.ld(base + AV_FAT_EMA);
+        fatEma += (instantFatigue - fatEma) * 0.06f;
+        m.fatigueRisk = jlimitf(0.0f, 1.0f, fatEma);
+
+        float score = 100.0f * (0.30f * m.punch + 0.25f * m.richness + 0.25f * m.clarity + 0.20f * m.width);
+        score *= (0.6f + 0.4f * m.monoSafety);
+        m.score = jlimitf(0.0f, 100.0f, score);
+
+        L.st(base + AV_SHORT, sEnv);
+        L.st(base + AV_LONG, lEnv);
+        L.st(base + AV_LOW, low);
+        L.st(base + AV_HIGH, high);
+        L.sti(base + AV_COOLDOWN, cool);
+        L.st(base + AV_REP_EMA, repEma);
+        L.st(base + AV_FAT_EMA, fatEma);
+        return m;
+    }
+};
+
+// Output parameter as the host reads it back: setValueNotifyingHost(convertTo0to1(v))
+// then the APVTS adapter's denormalise(getValue()) (e.g. JuicyPunch/PluginProcessor.cpp:56-62).
+__device__ __forceinline__ float output_param(float v, float lo, float hi)
+{
+    const float n = jlimitf(0.0f, 1.0f, (v - lo) / (hi - lo));
+    const float stored = jlimitf(lo, hi, lo + (hi - lo) * n);
+    const float n2 = jlimitf(0.0f, 1.0f, (stored - lo) / (hi - lo));
+    return jlimitf(lo, hi, lo + (hi - lo) * n2);
+}
+
+__device__ void write_record(const ProcArgs& a, int slot, long long clip, int blockAbs, const float* rec)
+{
+    float* dst = a.latest + (long long) slot * JBK_REC * a.clipPitch + clip;
+#pragma unroll
+    for (int f = 0; f < JBK_REC; ++f)
+        dst[(long long) f * a.clipPitch] = rec[f];
+    if (a.hist != nullptr && blockAbs < a.histMaxBlocks) {
+        float* h = a.hist + ((long long) blockAbs * a.chainLen + slot) * JBK_REC * a.clipPitch + clip;
+#pragma unroll
+        for (int f = 0; f < JBK_REC; ++f)
+            h[(long long) f * a.clipPitch] = rec[f];
+    }
+}
+
+// getLatestMetrics() of the ordinary plugins: 8 mailboxes (e.g. JuicyPunch/PluginProcessor.cpp:115-123,190-202)
+__device__ void publish_plain(const ProcArgs& a, int slot, long long clip, int blockAbs, const Metrics& m, float preScore, float aux)
+{
+    float rec[JBK_REC];
+    rec[0] = m.score; rec[1] = preScore; rec[2] = m.score;
+    rec[3] = 0.0f; rec[4] = 0.0f; rec[5] = 0.0f; rec[6] = 0.0f; rec[7] = 0.0f;
+    rec[8] = m.punch; rec[9] = m.richness; rec[10] = m.clarity; rec[11] = m.width; rec[12] = m.monoSafety;
+    rec[13] = output_param(m.score, 0.0f, 100.0f);
+    rec[14] = aux;
+    rec[15] = 0.0f;
+    write_record(a, slot, clip, blockAbs, rec);
+}
+
+// ------------------------------------------------------------------ plugin DSP ("main" part of a sweep)
+// Interface: writes() (must the sweep store samples), kSeqChannels (channel 0's whole block
+// must precede channel 1's), load/store of per-clip state, step(l, r) in place.
+
+struct MainBase {
+    __device__ __forceinline__ float stepCh0(float l) { return l; }
+    __device__ __forceinline__ bool writes(bool outOfPlace) const { return true; }
+};
+
+struct MainNone : MainBase { // sweep 0: samples pass through untouched, nothing to publish
+    static constexpr bool kHas = false, kSeqChannels = false;
+    __device__ __forceinline__ void load(const Lane&, const SlotDesc&, int) {}
+    __device__ __forceinline__ void step(float&, float&) {}
+    __device__ __forceinline__ void store(const Lane&, const SlotDesc&) {}
+};
+
+// JuicyInfer/PluginProcessor.cpp:78-81: buffer.applyGain(trimGain) between the two analyses
+struct MainInfer : MainBase {
+    static constexpr bool kHas = true, kSeqChannels = false;
+    float g;
+    int mode;
+    __device__ __forceinline__ void load(const Lane&, const SlotDesc& d, int)
+    {
+        g = d.c.infer.trimGain;
+        mode = d.c.infer.gainMode;
+    }
+    __device__ __forceinline__ void step(float& l, float& r)
+    {
+        if (mode == 1) {
+            l *= g;
+            r *= g;
+        } else if (mode == 2) {
+            l = 0.0f;
+            r = 0.0f;
+        }
+    }
+    __device__ __forceinline__ void store(const Lane&, const SlotDesc&) {}
+    __device__ __forceinline__ bool writes(bool outOfPlace) const { return mode != 0 || outOfPlace; }
+};
+
+// JuicySaturator/PluginProcessor.cpp:83-98
+struct MainSat : MainBase {
+    static constexpr bool kHas = true, kSeqChannels = false;
+    float s0, s1;
+    SatCoef c;
+    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
+    {
+        c = d.c.sat;
+        const int b = d.stateBase + AV_COUNT;
+        s0 = L.ld(b + SV_TONE0);
+        s1 = L.ld(b + SV_TONE1);
+    }
+    __device__ __forceinline__ float one(float dry, float& state) const
+    {
+        const float driven = dry * c.inGain;
+        const float skewed = driven + c.asym * driven * driven;
+        const float soft = tanhf(skewed);
+        state += c.toneCoeff * (soft - state);
+        const float wet = state * c.outGain;
+        return dry + c.mix * (wet - dry);
+    }
+    __device__ __forceinline__ void step(float& l, float& r)
+    {
+        l = one(l, s0);
+        r = one(r, s1);
+    }
+    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
+    {
+        const int b = d.stateBase + AV_COUNT;
+        L.st(b + SV_TONE0, s0);
+        L.st(b + SV_TONE1, s1);
+    }
+};
+
+// JuicyPunch/PluginProcessor.cpp:86-112
+struct MainPunch : MainBase {
+    static constexpr bool kHas = true, kSeqChannels = false;
+    float f0, f1, sl0, sl1;
+    PunchCoef c;
+    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
+    {
+        c = d.c.punch;
+        const int b = d.stateBase + AV_COUNT;
+        f0 = L.ld(b + PV_FAST0);
+        f1 = L.ld(b + PV_FAST1);
+        sl0 = L.ld(b + PV_SLOW0);
+        sl1 = L.ld(b + PV_SLOW1);
+    }
+    __device__ __forceinline__ float one(float dry, float& fEnv, float& sEnv) const
+    {
+        const float adry = fabsf(dry);
+        fEnv = c.omFast * adry + c.fastCoeff * fEnv;
+        sEnv = c.omSlow * adry + c.slowCoeff * sEnv;
+        const float transient = jmaxf(0.0f, fEnv - sEnv);
+        const float transientCurve = powf(transient, c.curveExp);
+        const float punchGain = 1.0f + c.punchK * transientCurve;
+        const float sustainGain = 1.0f + c.sustainK * jmaxf(0.0f, sEnv - transient * 0.6f);
+        float wet = dry * punchGain * sustainGain;
+        const float soft = tanhf(wet * c.drive) / c.tanhDrive;
+        const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
+        wet = soft + c.clipAmt * (hard - soft);
+        return (dry + c.mix * (wet - dry)) * c.outGain;
+    }
+    __device__ __forceinline__ void step(float& l, float& r)
+    {
+        l = one(l, f0, sl0);
+        r = one(r, f1, sl1);
+    }
+    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
+    {
+        const int b = d.stateBase + AV_COUNT;
+        L.st(b + PV_FAST0, f0);
+        L.st(b + PV_FAST1, f1);
+        L.st(b + PV_SLOW0, sl0);
+        L.st(b + PV_SLOW1, sl1);
+    }
+};
+
+// JuicyWidth/PluginProcessor.cpp:91-137.  The delay line keeps only the right
+// channel's wet signal (the left ring is written but never read, :122,:131) in a
+// time-major ring [ringLen][clip], so a warp's accesses coalesce.
+struct MainWidth : MainBase {
+    static constexpr bool kHas = true, kSeqChannels = false;
+    float width;
+    int wpos;
+    WidthCoef c;
+    float* ring;
+    long long pitch;
+    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
+    {
+        c = d.c.width;
+        width = c.width; // re-read from the parameter every block (:93)
+        wpos = L.ldi(d.stateBase + AV_COUNT + WV_WPOS);
+        ring = L.a.widthRing + L.clip;
+        pitch = L.a.clipPitch;
+    }
+    __device__ __forceinline__ void step(float& l, float& r)
+    {
+        const float dryL = l, dryR = r;
+        const float corrProxy = jlimitf(-1.0f, 1.0f, dryL * dryR * 12.0f);
+        if (corrProxy < -0.1f)
+            width *= c.dynamicLimit;
+        const float mid = 0.5f * (dryL + dryR);
+        const float side = 0.5f * (dryL - dryR) * (1.0f + width);
+        const float wetL = mid + side;
+        float wetR = mid - side;
+        ring[(long long) wpos * pitch] = wetR;
+        int readPos = wpos - c.delaySamples;
+        if (readPos < 0)
+            readPos += c.ringLen;
+        wetR = ring[(long long) readPos * pitch];
+        l = (dryL + c.mix * (wetL - dryL)) * c.outGain;
+        r = (dryR + c.mix * (wetR - dryR)) * c.outGain;
+        if (++wpos >= c.ringLen)
+            wpos = 0;
+    }
+    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d) { L.sti(d.stateBase + AV_COUNT + WV_WPOS, wpos); }
+};
+
+// JuicyCohere/PluginProcessor.cpp:99-119 (lpA/lpB restart at 0 every block, :103-104)
+struct MainCohere : MainBase {
+    static constexpr bool kHas = true, kSeqChannels = false;
+    float t0, t1, a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+    float lowComp, midComp, highComp;
+    CohereCoef c;
+    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
+    {
+        c = d.c.cohere;
+        const int b = d.stateBase + AV_COUNT;
+        t0 = L.ld(b + CV_TAIL0);
+        t1 = L.ld(b + CV_TAIL1);
+        lowComp = L.ld(b + CV_COMP_LOW);
+        midComp = L.ld(b + CV_COMP_MID);
+        highComp = L.ld(b + CV_COMP_HIGH);
+    }
+    __device__ __forceinline__ float one(float dry, float& lpA, float& lpB, float& tail) const
+    {
+        lpA += c.lowCoeff * (dry - lpA);
+        lpB += c.highCoeff * (dry - lpB);
+        const float low = lpA * lowComp;
+        const float high = (dry - lpB) * highComp;
+        const float mid = (dry - lpA - (dry - lpB)) * midComp;
+        const float matched = low + mid + high;
+        tail = matched + tail * c.fb;
+        const float wet = matched + c.tailK * tail;
+        return (dry + c.mix * (wet - dry)) * c.outGain;
+    }
+    __device__ __forceinline__ void step(float& l, float& r)
+    {
+        l = one(l, a0, b0, t0);
+        r = one(r, a1, b1, t1);
+    }
+    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
+    {
+        const int b = d.stateBase + AV_COUNT;
+        L.st(b + CV_TAIL0, t0);
+        L.st(b + CV_TAIL1, t1);
+    }
+};
+
+// JuicyTexture ChannelState (JuicyTexture/PluginProcessor.h:55-77) held in registers
+struct TexChan {
+    float tail, lp, hp, env, wetEnv, noiseHp, dcIn, dcOut, protectGain, springPos, springVel;
+    float fleshPosA, fleshVelA, fleshPosB, fleshVelB, prevWave;
+    float y1[4], y2[4];
+    __device__ __forceinline__ void load(const Lane& L, int b)
+    {
+        tail = L.ld(b + TV_TAIL); lp = L.ld(b + TV_LP); hp = L.ld(b + TV_HP); env = L.ld(b + TV_ENV);
+        wetEnv = L.ld(b + TV_WETENV); noiseHp = L.ld(b + TV_NOISEHP); dcIn = L.ld(b + TV_DCIN); dcOut = L.ld(b + TV_DCOUT);
+        protectGain = L.ld(b + TV_PROTECT); springPos = L.ld(b + TV_SPRING_POS); springVel = L.ld(b + TV_SPRING_VEL);
+        fleshPosA = L.ld(b + TV_FLESH_PA); fleshVelA = L.ld(b + TV_FLESH_VA); fleshPosB = L.ld(b + TV_FLESH_PB);
+        fleshVelB = L.ld(b + TV_FLESH_VB); prevWave = L.ld(b + TV_PREVWAVE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            y1[k] = L.ld(b + TV_Y1_0 + k);
+            y2[k] = L.ld(b + TV_Y2_0 + k);
+        }
+    }
+    __device__ __forceinline__ void store(const Lane& L, int b) const
+    {
+        L.st(b + TV_TAIL, tail); L.st(b + TV_LP, lp); L.st(b + TV_HP, hp); L.st(b + TV_ENV, env);
+        L.st(b + TV_WETENV, wetEnv); L.st(b + TV_NOISEHP, noiseHp); L.st(b + TV_DCIN, dcIn); L.st(b + TV_DCOUT, dcOut);
+        L.st(b + TV_PROTECT, protectGain); L.st(b + TV_SPRING_POS, springPos); L.st(b + TV_SPRING_VEL, springVel);
+        L.st(b + TV_FLESH_PA, fleshPosA); L.st(b + TV_FLESH_VA, fleshVelA); L.st(b + TV_FLESH_PB, fleshPosB);
+        L.st(b + TV_FLESH_VB, fleshVelB); L.st(b + TV_PREVWAVE, prevWave);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            L.st(b + TV_Y1_0 + k, y1[k]);
+            L.st(b + TV_Y2_0 + k, y2[k]);
+        }
+    }
+};
+
+// JuicyTexture/PluginProcessor.cpp:107-278, one material per instantiation.
+// The LCG `rng` is one instance member advanced by channel 0's whole block and
+// then by channel 1's (:107,:114,:239); channel 1 therefore starts n draws ahead
+// (affine skip-ahead), which lets both channels run sample-interleaved.
+template <int MAT>
+struct MainTexture : MainBase {
+    static constexpr bool kHas = true, kSeqChannels = false;
+    TexChan ch0, ch1;
+    uint32_t rng0, rng1;
+    int waveIdx;
+    const TexCoef* c;
+    float* wave;
+    long long pitch;
+
+    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int n)
+    {
+        c = &d.c.tex;
+        const int b = d.stateBase + AV_COUNT;
+        ch0.load(L, b);
+        ch1.load(L, b + TV_CH_STRIDE);
+        waveIdx = L.ldi(b + TV_WAVEIDX);
+        rng0 = (uint32_t) L.ldi(b + TV_RNG);
+        uint32_t A = 1664525u, C = 1013904223u, accA = 1u, accC = 0u; // x -> A^n x + C_n
+        for (int k = n; k > 0; k >>= 1) {
+            if (k & 1) {
+                accA *= A;
+                accC = accC * A + C;
+            }
+            C = (A + 1u) * C;
+            A *= A;
+        }
+        rng1 = accA * rng0 + accC;
+        wave = L.a.texWave + L.clip;
+        pitch = L.a.clipPitch;
+    }
+
+    // modeStep with block-constant pole radius (:77-89); a1 is passed in
+    __device__ __forceinline__ float mode(TexChan& st, int k, float exc, float a1) const
+    {
+        const float y = exc * c->modeGain[k] + a1 * st.y1[k] + c->modeA2[k] * st.y2[k];
+        st.y2[k] = st.y1[k];
+        st.y1[k] = y;
+        return y;
+    }
+    __device__ __forceinline__ float metalA1(int k, float bend) const
+    {
+        const float f = jlimitf(20.0f, c->fMax, c->modeF[k] * bend);
+        const float theta = 2.0f * PI_F * f / c->srf;
+        return c->modeTwoR[k] * cos_exact(theta);
+    }
+    // waveguideRead (:91-105) on the time-major ring of this channel
+    __device__ __forceinline__ float waveRead(const float* line) const
+    {
+        const int size = c->waveSize;
+        float pos = (float) waveIdx - c->delaySamp;
+        while (pos < 0.0f)
+            pos += (float) size;
+        while (pos >= (float) size)
+            pos -= (float) size;
+        const int i0 = (int) pos;
+        const int i1 = (i0 + 1) % size;
+        const float frac = pos - (float) i0;
+        return jmap3(frac, line[(long long) i0 * pitch], line[(long long) i1 * pitch]);
+    }
+
+    __device__ __forceinline__ float one(float dry, TexChan& st, uint32_t& rng, float* line) const
+    {
+        const TexCoef& k = *c;
+        const float driven = dry * k.inTrim;
+        const float adry = fabsf(dry);
+        {
+            const bool up = adry > st.env;
+            st.env = (up ? k.envAtk : k.envRel) * st.env + (up ? k.omEnvAtk : k.omEnvRel) * adry;
+        }
+        const float impact = jlimitf(0.0f, 1.0f, jmaxf(0.0f, adry - st.env) * 10.0f);
+        const float body = jlimitf(0.0f, 1.0f, st.env * 3.2f);
+        const float trail = jlimitf(0.0f, 1.0f, 1.0f - impact) * k.tailShape;
+
+        st.lp += k.splitLow * (driven - st.lp);
+        st.hp += k.splitHigh * (driven - st.hp);
+        const float low = st.lp * k.lowBoost;
+        const float high = (driven - st.hp);
+        const float mid = driven - st.lp - high;
+        const float core = low + mid + high * k.highTilt;
+
+        float shaped;
+        if (MAT == 0) { // gel :137-151
+            const float zeta = jmap3(trail, 0.62f, 1.45f);
+            const float cc = 2.0f * zeta * k.gelOmega;
+            const float force = core * (0.52f + 0.62f * body);
+            const float acc = k.gelK * (force - st.springPos) - cc * st.springVel;
+            st.springVel += acc;
+            st.springPos += st.springVel;
+            shaped = 0.48f * core + 1.85f * st.springPos;
+            shaped = tanhf(shaped * k.shapeGain);
+        } else if (MAT == 1) { // metal :152-169
+            const float exc = core * (0.19f + 0.52f * impact);
+            const float bend = 1.0f + 0.09f * impact;
+            const float m0 = mode(st, 0, exc, metalA1(0, bend));
+            const float m1 = mode(st, 1, exc, metalA1(1, bend));
+            const float m2 = mode(st, 2, exc, metalA1(2, bend));
+            const float m3 = mode(st, 3, exc, metalA1(3, bend));
+            const float modes = m0 + m1 + m2 + m3;
+            const float brightExcite = 0.03f * impact * (core - st.hp);
+            shaped = (0.44f * core + 0.42f * modes + brightExcite) * k.shapeGain;
+        } else if (MAT == 2 || MAT == 3) { // wood :170-192, plastic :193-213
+            const float exc = core * (k.excA + k.excB * impact);
+            const float delayed = waveRead(line);
+            float newWave;
+            if (MAT == 2)
+                newWave = k.waveDamp * (0.62f * delayed + 0.38f * st.prevWave) + exc * (0.09f + 0.04f * body);
+            else
+                newWave = k.waveDamp * (0.76f * delayed + 0.24f * st.prevWave) + 0.14f * exc;
+            line[(long long) waveIdx * pitch] = newWave;
+            st.prevWave = delayed;
+            const float w0 = mode(st, 0, exc, k.modeA1[0]);
+            const float w1 = mode(st, 1, exc, k.modeA1[1]);
+            const float w2 = mode(st, 2, exc, k.modeA1[2]);
+            const float w3 = mode(st, 3, exc, k.modeA1[3]);
+            shaped = (k.waveMixA * core + k.waveMixB * delayed + k.waveOut * (w0 + w1 + w2 + w3)) * k.shapeGain;
+        } else { // flesh :214-236
+            const float force = core * (0.55f + 0.65f * body);
+            const float accA = k.kA * (force - st.fleshPosA) - k.cA * st.fleshVelA - k.kCouple * (st.fleshPosA - st.fleshPosB);
+            const float accB = k.kB * (st.fleshPosA - st.fleshPosB) - k.cB * st.fleshVelB;
+            st.fleshVelA += accA;
+            st.fleshVelB += accB;
+            st.fleshPosA += st.fleshVelA;
+            st.fleshPosB += st.fleshVelB;
+            const float tissue = 0.92f * st.fleshPosA + 0.58f * st.fleshPosB;
+            const float nl = tissue - 0.19f * tissue * tissue * tissue;
+            shaped = tanhf((0.50f * core + 1.34f * nl) * k.shapeGain);
+        }
+
+        rng = 1664525u * rng + 1013904223u; // :239-243
+        const float white = ((float) ((rng >> 8) & 0xFFFFu) / 32768.0f - 1.0f);
+        st.noiseHp += 0.08f * (white - st.noiseHp);
+        const float rough = white - st.noiseHp;
+        shaped += rough * k.noiseAmt * (0.14f + 0.64f * impact);
+
+        const float dynamics = 1.0f + impact * k.dynK + body * 0.06f;
+        shaped *= dynamics * k.matTrim;
+
+        const float tailInput = jlimitf(-2.0f, 2.0f, shaped) * (0.45f + 0.55f * trail);
+        st.tail = tailInput + st.tail * k.decay;
+        float wet = shaped + st.tail * (0.30f + 0.45f * trail);
+
+        const float wetAbs = fabsf(wet); // :253-257
+        {
+            const bool up = wetAbs > st.wetEnv;
+            st.wetEnv = (up ? k.wetAtk : k.wetRel) * st.wetEnv + (up ? k.omWetAtk : k.omWetRel) * wetAbs;
+        }
+        const float autoComp = k.autoGainBase / (1.0f + 1.8f * st.wetEnv);
+        wet *= jlimitf(0.18f, 1.0f, autoComp);
+
+        const float mixed = dry + k.mix * (wet - dry);
+        float out = mixed * k.outGain;
+
+        const float dcBlocked = out - st.dcIn + 0.995f * st.dcOut; // :263-265
+        st.dcIn = out;
+        st.dcOut = dcBlocked;
+
+        const float peak = fabsf(dcBlocked); // :268-276
+        if (peak > 0.88f)
+            st.protectGain = jminf(st.protectGain, (0.88f / peak) * 0.98f);
+        else
+            st.protectGain += (1.0f - st.protectGain) * 0.0028f;
+        out = dcBlocked * jlimitf(0.2f, 1.0f, st.protectGain);
+        return jlimitf(-0.98f, 0.98f, out);
+    }
+
+    __device__ __forceinline__ void step(float& l, float& r)
+    {
+        float* line0 = wave;
+        float* line1 = wave + (long long) c->waveSize * pitch;
+        l = one(l, ch0, rng0, line0);
+        r = one(r, ch1, rng1, line1);
+        if (MAT == 2 || MAT == 3)
+            waveIdx = (waveIdx + 1) % c->waveSize;
+    }
+    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
+    {
+        const int b = d.stateBase + AV_COUNT;
+        ch0.store(L, b);
+        ch1.store(L, b + TV_CH_STRIDE);
+        L.sti(b + TV_WAVEIDX, waveIdx);
+        L.sti(b + TV_RNG, (int) rng1); // state after both channels' draws
+    }
+};
+
+// JuicyMotion/PluginProcessor.cpp:101-142.  variation*, motionPhase and budgetEnv
+// are instance members walked by channel 0's whole block and then channel 1's, so
+// the main part runs as two sequential channel passes (kSeqChannels).
+struct MainMotion : MainBase {
+    static constexpr bool kHas = true, kSeqChannels = true;
+    float vTone, vTrans, vTail, tTone, tTrans, tTail, phase, budget;
+    float tail0, tail1, lp0, lp1, prev0, prev1, repScale, recovery;
+    MotionCoef c;
+    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
+    {
+        c = d.c.motion;
+        const int b = d.stateBase + AV_COUNT;
+        vTone = L.ld(b + MV_VTONE); vTrans = L.ld(b + MV_VTRANS); vTail = L.ld(b + MV_VTAIL);
+        tTone = L.ld(b + MV_TTONE); tTrans = L.ld(b + MV_TTRANS); tTail = L.ld(b + MV_TTAIL);
+        phase = L.ld(b + MV_PHASE); budget = L.ld(b + MV_BUDGET);
+        tail0 = L.ld(b + MV_TAIL0); tail1 = L.ld(b + MV_TAIL1);
+        lp0 = L.ld(b + MV_LP0); lp1 = L.ld(b + MV_LP1);
+        prev0 = L.ld(b + MV_PREV0); prev1 = L.ld(b + MV_PREV1);
+        repScale = L.ld(b + MV_REP_SCALE); recovery = L.ld(b + MV_RECOVERY);
+    }
+    __device__ __forceinline__ float one(float dry, float lfoOffset, float& tail, float& lp, float& prev)
+    {
+        vTone = c.varSlew * vTone + c.omVarSlew * tTone;
+        vTrans = c.varSlew * vTrans + c.omVarSlew * tTrans;
+        vTail = c.varSlew * vTail + c.omVarSlew * tTail;
+        phase += c.motionInc;
+        if (phase > 2.0f * PI_F)
+            phase -= 2.0f * TWO_PI_F; // sic (:114-115)
+
+        const float motionLfo = sinf(phase + lfoOffset);
+        const float cutoff = jlimitf(120.0f, 4200.0f, 900.0f + vTone * 1100.0f * c.d06 + motionLfo * c.lfoDepth);
+        const float lpCoeff = 1.0f - expf(-2.0f * PI_F * cutoff / c.srf);
+        lp += lpCoeff * (dry - lp);
+        const float hp = dry - lp;
+        const float transient = dry - prev;
+        prev = dry;
+
+        const float transientBoost = 1.0f + vTrans * 1.2f * c.d07 + c.mv035 * motionLfo * c.d08;
+        const float toneShift = lp * (1.0f + vTone * 0.65f * c.d0507) + hp * transientBoost + transient * c.mvT * c.d0508;
+        tail = toneShift + tail * jlimitf(0.0f, 0.93f, c.tailFeedback + vTail * 0.06f);
+
+        float wet = toneShift * repScale * recovery + c.tailMix * tail;
+        budget = c.budgetCoeff * budget + c.omBudget * fabsf(wet);
+        const float limiterGain = budget > c.budgetTarget ? c.budgetTarget / (budget + 1.0e-5f) : 1.0f;
+        wet *= limiterGain;
+        return (dry + c.mix * (wet * c.wetBoost - dry)) * c.outGain;
+    }
+    __device__ __forceinline__ float stepCh0(float l) { return one(l, 0.0f, tail0, lp0, prev0); }
+    __device__ __forceinline__ void step(float&, float& r) { r = one(r, 0.85f, tail1, lp1, prev1); }
+    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
+    {
+        const int b = d.stateBase + AV_COUNT;
+        L.st(b + MV_VTONE, vTone); L.st(b + MV_VTRANS, vTrans); L.st(b + MV_VTAIL, vTail);
+        L.st(b + MV_PHASE, phase); L.st(b + MV_BUDGET, budget);
+        L.st(b + MV_TAIL0, tail0); L.st(b + MV_TAIL1, tail1);
+        L.st(b + MV_LP0, lp0); L.st(b + MV_LP1, lp1);
+        L.st(b + MV_PREV0, prev0); L.st(b + MV_PREV1, prev1);
+    }
+};
+
+// ------------------------------------------------------------------ block pre-passes of the NEXT plugin
+
+struct PreNone { // no next plugin
+    static constexpr bool kHas = false;
+    __device__ __forceinline__ void load(const Lane&, const SlotDesc&) {}
+    __device__ __forceinline__ void step(float, float, float) {}
+    __device__ __forceinline__ void finish(const Lane&, const SlotDesc&, int) {}
+};
+struct PreAna { // next plugin needs only its analyzer's pre pass
+    static constexpr bool kHas = true;
+    __device__ __forceinline__ void load(const Lane&, const SlotDesc&) {}
+    __device__ __forceinline__ void step(float, float, float) {}
+    __device__ __forceinline__ void finish(const Lane&, const SlotDesc&, int) {}
+};
+
+// JuicyCohere/PluginProcessor.cpp:62-96: band energies of the block's mono sum through
+// the persistent 220/2400 Hz one-poles, optional target learning, context fit and
+// the three compensation gains used by the main loop.
+struct PreCohere {
+    static constexpr bool kHas = true;
+    float lowLp, highLp, eLow = 0.0f, eMid = 0.0f, eHigh = 0.0f;
+    CohereCoef c;
+    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d)
+    {
+        c = d.c.cohere;
+        const int b = d.stateBase + AV_COUNT;
+        lowLp = L.ld(b + CV_LOWLP);
+        highLp = L.ld(b + CV_HIGHLP);
+    }
+    __device__ __forceinline__ void step(float, float, float mono)
+    {
+        lowLp += c.lowCoeff * (mono - lowLp);
+        highLp += c.highCoeff * (mono - highLp);
+        const float low = lowLp;
+        const float high = mono - highLp;
+        const float mid = mono - low - high;
+        eLow += low * low;
+        eMid += mid * mid;
+        eHigh += high * high;
+    }
+    static __device__ __forceinline__ float gainToDb(float g) { return g > 0.0f ? jmaxf(-100.0f, log10_exact(g) * 20.0f) : -100.0f; }
+    __device__ void finish(const Lane& L, const SlotDesc& d, int n)
+    {
+        const int b = d.stateBase + AV_COUNT;
+        const float inv = 1.0f / (float) (n > 1 ? n : 1);
+        eLow *= inv;
+        eMid *= inv;
+        eHigh *= inv;
+        float tLow = L.ld(b + CV_TGT_LOW), tMid = L.ld(b + CV_TGT_MID), tHigh = L.ld(b + CV_TGT_HIGH);
+        if (c.learn) {
+            tLow += (eLow - tLow) * 0.02f;
+            tMid += (eMid - tMid) * 0.02f;
+            tHigh += (eHigh - tHigh) * 0.02f;
+            L.st(b + CV_TGT_LOW, tLow);
+            L.st(b + CV_TGT_MID, tMid);
+            L.st(b + CV_TGT_HIGH, tHigh);
+        }
+        const float lowErr = fabsf(gainToDb((eLow + 1.0e-6f) / (tLow + 1.0e-6f)));
+        const float midErr = fabsf(gainToDb((eMid + 1.0e-6f) / (tMid + 1.0e-6f)));
+        const float highErr = fabsf(gainToDb((eHigh + 1.0e-6f) / (tHigh + 1.0e-6f)));
+        const float deviation = (lowErr + midErr + highErr) / 3.0f;
+        const float contextFit = jlimitf(0.0f, 100.0f, 100.0f - deviation * 10.0f);
+        L.st(b + CV_FIT, output_param(contextFit, 0.0f, 100.0f));
+        L.st(b + CV_COMP_LOW, jlimitf(0.5f, 1.8f, pow_exact((tLow + 1.0e-6f) / (eLow + 1.0e-6f), c.matchQ)));
+        L.st(b + CV_COMP_MID, jlimitf(0.5f, 1.8f, pow_exact((tMid + 1.0e-6f) / (eMid + 1.0e-6f), c.matchQ)));
+        L.st(b + CV_COMP_HIGH, jlimitf(0.5f, 1.8f, pow_exact((tHigh + 1.0e-6f) / (eHigh + 1.0e-6f), c.matchQ)));
+        L.st(b + CV_LOWLP, lowLp);
+        L.st(b + CV_HIGHLP, highLp);
+    }
+};
+
+// JuicyMotion/PluginProcessor.cpp:75-99: onset detector over the block's mono sum,
+// LCG-drawn variation targets, repetition counter and the two block scalars.
+struct PreMotion {
+    static constexpr bool kHas = true;
+    float env, repetition, tTone, tTrans, tTail;
+    int cool;
+    uint32_t rng;
+    MotionCoef c;
+    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d)
+    {
+        c = d.c.motion;
+        const int b = d.stateBase + AV_COUNT;
+        env = L.ld(b + MV_ENV);
+        repetition = L.ld(b + MV_REPETITION);
+        tTone = L.ld(b + MV_TTONE);
+        tTrans = L.ld(b + MV_TTRANS);
+        tTail = L.ld(b + MV_TTAIL);
+        cool = L.ldi(b + MV_COOLDOWN);
+        rng = (uint32_t) L.ldi(b + MV_RNG);
+    }
+    __device__ __forceinline__ void step(float, float, float mono)
+    {
+        const float absMono = fabsf(mono);
+        env = c.envCoeff * env + c.omEnv * absMono;
+        if (cool > 0)
+            --cool;
+        if (absMono > env * 1.35f + 0.02f && cool <= 0) {
+            cool = c.cooldownLen;
+            repetition += 1.0f;
+            rng = 1664525u * rng + 1013904223u;
+            tTone = (((float) ((rng >> 7) & 0x7FFFu) / 16384.0f) - 1.0f) * c.microVar * 0.9f;
+            rng = 1664525u * rng + 1013904223u;
+            tTrans = (((float) ((rng >> 9) & 0x7FFFu) / 16384.0f) - 1.0f) * c.microVar * 0.8f;
+            rng = 1664525u * rng + 1013904223u;
+            tTail = (((float) ((rng >> 11) & 0x7FFFu) / 16384.0f) - 1.0f) * c.microVar * 0.8f;
+        }
+        repetition *= 0.997f;
+    }
+    __device__ void finish(const Lane& L, const SlotDesc& d, int)
+    {
+        const int b = d.stateBase + AV_COUNT;
+        const float repNorm = jlimitf(0.0f, 1.0f, repetition * 0.08f);
+        L.st(b + MV_REP_SCALE, 1.0f - c.repeatCtrl * repNorm * 0.65f);
+        L.st(b + MV_RECOVERY, 1.0f + c.repeatCtrl * (1.0f - repNorm) * 0.25f);
+        L.st(b + MV_ENV, env);
+        L.st(b + MV_REPETITION, repetition);
+        L.st(b + MV_TTONE, tTone);
+        L.st(b + MV_TTRANS, tTrans);
+        L.st(b + MV_TTAIL, tTail);
+        L.sti(b + MV_COOLDOWN, cool);
+        L.sti(b + MV_RNG, (int) rng);
+    }
+};
+
+// ------------------------------------------------------------------ sample access (v1: per-lane row streaming)
+
+struct Quad { float v[4]; };
+
+__device__ __forceinline__ Quad load4(const float* p, int i, int n, bool vec)
+{
+    Quad q;
+    if (vec && i + 4 <= n) {
+        const float4 t = *reinterpret_cast<const float4*>(p + i);
+        q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            q.v[k] = (i + k < n) ? p[i + k] : 0.0f;
+    }
+    return q;
+}
+__device__ __forceinline__ void store4(float* p, int i, int n, bool vec, const Quad& q)
+{
+    if (vec && i + 4 <= n) {
+        *reinterpret_cast<float4*>(p + i) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k < n)
+                p[i + k] = q.v[k];
+    }
+}
+
+// One sweep over one block of one clip.  mainSlot < 0 for sweep 0.
+template <class Main, class Pre>
+__device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
+{
+    const Lane L { a, clip };
+    const int preSlot = mainSlot + 1;
+    const bool firstRead = mainSlot <= 0; // sweep 0 and plugin 0's sweep read the caller's input
+    const long long rowL = (clip * a.nCh) * (long long) a.nSamples + pos;
+    const long long rowR = rowL + a.nSamples;
+    const float* srcL = (firstRead ? a.in : a.out) + rowL;
+    const float* srcR = (firstRead ? a.in : a.out) + rowR;
+    float* dstL = a.out + rowL;
+    float* dstR = a.out + rowR;
+    const bool vec = a.vecOk != 0;
+
+    Main mainPart;
+    AnaWalk post, pre;
+    Pre prePart;
+    BlockStats stats;
+    const AnaCoef ana = a.ana;
+    bool mustWrite = false;
+    if constexpr (Main::kHas) {
+        mainPart.load(L, a.slot[mainSlot], n);
+        post.load(L, a.slot[mainSlot].stateBase);
+        mustWrite = mainPart.writes(a.in != a.out);
+    }
+    if constexpr (Pre::kHas) {
+        pre.load(L, a.slot[preSlot].stateBase);
+        prePart.load(L, a.slot[preSlot]);
+    }
+
+    if constexpr (Main::kSeqChannels) { // Motion: channel 0's block first
+        for (int i = 0; i < n; i += 4) {
+            Quad q = load4(srcL, i, n, vec);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i + k < n)
+                    q.v[k] = mainPart.stepCh0(q.v[k]);
+            store4(dstL, i, n, vec, q);
+        }
+        srcL = dstL;
+    }
+
+    for (int i = 0; i < n; i += 4) {
+        Quad ql = load4(srcL, i, n, vec);
+        Quad qr = load4(srcR, i, n, vec);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < n) {
+                float l = ql.v[k], r = qr.v[k];
+                mainPart.step(l, r);
+                const float mono = 0.5f * (l + r);
+                stats.step(l, r, mono);
+                if constexpr (Main::kHas)
+                    post.step(mono, ana);
+                if constexpr (Pre::kHas) {
+                    pre.step(mono, ana);
+                    prePart.step(l, r, mono);
+                }
+                ql.v[k] = l;
+                qr.v[k] = r;
+            }
+        }
+        if (mustWrite) {
+            if (!Main::kSeqChannels)
+                store4(dstL, i, n, vec, ql);
+            store4(dstR, i, n, vec, qr);
+        }
+    }
+
+    if constexpr (Main::kHas) {
+        const SlotDesc& d = a.slot[mainSlot];
+        mainPart.store(L, d);
+        Metrics m = post.finish(L, d.stateBase, stats, n, ana);
+        const float preScore = L.ld(d.stateBase + AV_PRE_SCORE);
+        if (d.kind == K_INFER) { // JuicyInfer/PluginProcessor.cpp:81-101,164-181
+            m.score = jlimitf(0.0f, 100.0f, m.score * d.c.infer.sensitivity);
+            float rec[JBK_REC];
+            rec[0] = m.score; rec[1] = preScore; rec[2] = m.score;
+            rec[3] = m.emphasis; rec[4] = m.coherence; rec[5] = m.synesthesia; rec[6] = m.fatigueRisk; rec[7] = m.repetitionDensity;
+            rec[8] = m.emphasis; rec[9] = m.coherence; rec[10] = m.synesthesia; rec[11] = m.fatigueRisk; rec[12] = m.repetitionDensity;
+            rec[13] = output_param(m.score, 0.0f, 100.0f);
+            rec[14] = 0.0f; rec[15] = 0.0f;
+            write_record(a, mainSlot, clip, blockAbs, rec);
+        } else {
+            const float aux = d.kind == K_COHERE ? L.ld(d.stateBase + AV_COUNT + CV_FIT) : 0.0f;
+            publish_plain(a, mainSlot, clip, blockAbs, m, preScore, aux);
+        }
+    }
+    if constexpr (Pre::kHas) {
+        const SlotDesc& d = a.slot[preSlot];
+        const Metrics m = pre.finish(L, d.stateBase, stats, n, ana);
+        L.st(d.stateBase + AV_PRE_SCORE, m.score);
+        prePart.finish(L, d, n);
+    }
+}
+
+template <class Main>
+__device__ __forceinline__ void sweep_pre_dispatch(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
+{
+    const int preSlot = mainSlot + 1;
+    if (preSlot >= a.chainLen) {
+        sweep<Main, PreNone>(a, clip, mainSlot, pos, n, blockAbs);
+        return;
+    }
+    switch (a.slot[preSlot].kind) {
+        case K_COHERE: sweep<Main, PreCohere>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_MOTION: sweep<Main, PreMotion>(a, clip, mainSlot, pos, n, blockAbs); break;
+        default: sweep<Main, PreAna>(a, clip, mainSlot, pos, n, blockAbs); break;
+    }
+}
+
+__device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
+{
+    if (mainSlot < 0) {
+        sweep_pre_dispatch<MainNone>(a, clip, mainSlot, pos, n, blockAbs);
+        return;
+    }
+    const SlotDesc& d = a.slot[mainSlot];
+    switch (d.kind) {
+        case K_INFER: sweep_pre_dispatch<MainInfer>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_PUNCH: sweep_pre_dispatch<MainPunch>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_SAT: sweep_pre_dispatch<MainSat>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_WIDTH: sweep_pre_dispatch<MainWidth>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_COHERE: sweep_pre_dispatch<MainCohere>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_MOTION: sweep_pre_dispatch<MainMotion>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_TEXTURE:
+            switch (d.c.tex.material) {
+                case 0: sweep_pre_dispatch<MainTexture<0>>(a, clip, mainSlot, pos, n, blockAbs); break;
+                case 1: sweep_pre_dispatch<MainTexture<1>>(a, clip, mainSlot, pos, n, blockAbs); break;
+                case 2: sweep_pre_dispatch<MainTexture<2>>(a, clip, mainSlot, pos, n, blockAbs); break;
+                case 3: sweep_pre_dispatch<MainTexture<3>>(a, clip, mainSlot, pos, n, blockAbs); break;
+                default: sweep_pre_dispatch<MainTexture<4>>(a, clip, mainSlot, pos, n, blockAbs); break;
+            }
+            break;
+        default: break;
+    }
+}
+
+#define JB_CTA_THREADS 32
+
+__global__ void __launch_bounds__(JB_CTA_THREADS) jb_process_kernel(const __grid_constant__ ProcArgs a)
+{
+    const long long clip = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (clip >= a.nClips)
+        return;
+    int blockAbs = a.histFirstBlock;
+    for (int pos = 0; pos < a.nSamples; pos += a.blockSize, ++blockAbs) {
+        const int n = min(a.blockSize, a.nSamples - pos);
+        for (int s = -1; s < a.chainLen; ++s)
+            sweep_dispatch(a, clip, s, pos, n, blockAbs);
+    }
+}
+
+__global__ void jb_fill_kernel(float* dst, float value, long long count)
+{
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        dst[i] = value;
+}
+
+// ------------------------------------------------------------------ synthetic clips
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// uniform in [-1, 1), exactly representable
+__device__ __forceinline__ float unit_noise(uint32_t seed, uint32_t ch, uint32_t n)
+{
+    const uint32_t h = hash32(seed ^ hash32(n * 2u + ch + 0x9E3779B9u));
+    return (float) (h >> 8) * (1.0f / 8388608.0f) - 1.0f;
+}
+
+__global__ void jb_synth_kernel(float* audio, int kind, long long firstClip, int nClips, int nCh, int nSamples,
+                                float sr, uint32_t baseSeed)
+{
+    const long long total = (long long) nClips * nSamples;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long idx = (long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int clipLocal = (int) (idx / nSamples);
+        const int n = (int) (idx - (long long) clipLocal * nSamples);
+        const long long clipId = firstClip + clipLocal;
+        const uint32_t seed = baseSeed ^ ((uint32_t) clipId * 0x9E3779B9u);
+        const int k = kind == 4 ? (int) (clipId & 3) : kind;
+        float l = 0.0f, r = 0.0f;
+        if (k == 0) { // exponential sine sweep 20 Hz -> 20 kHz over the clip, R 0.3 rad ahead
+            const float T = (float) nSamples / sr;
+            const float K = logf(1000.0f);
+            const float t = (float) n / sr;
+            const float ph = 2.0f * PI_F * 20.0f * T / K * (expf(t / T * K) - 1.0f);
+            l = 0.5f * sinf(ph);
+            r = 0.5f * sinf(ph + 0.3f);
+        } else if (k == 1) { // white noise +-0.25, R = 0.5 (L + independent)
+            l = 0.25f * unit_noise(seed, 0u, (uint32_t) n);
+            r = 0.5f * (l + 0.25f * unit_noise(seed, 1u, (uint32_t) n));
+        } else if (k == 2) { // impulse train, period 2400 + 37 (clip mod 64), R 7 samples late
+            const int period = 2400 + 37 * (int) (clipId & 63);
+            l = (n % period) == 0 ? 0.9f : 0.0f;
+            r = (n >= 7 && ((n - 7) % period) == 0) ? 0.9f : 0.0f;
+        } else { // drum hit
+            const uint32_t h = hash32(seed);
+            const int onset = 480 + (int) (h % 4800u);
+            const float f0 = 45.0f + 45.0f * (float) ((h >> 13) & 1023u) / 1023.0f;
+            if (n >= onset) {
+                const float m = (float) (n - onset);
+                const float body = 0.8f * expf(-m / 2400.0f) * sinf(2.0f * PI_F * f0 * m / sr);
+                const float burst = 0.4f * expf(-m / 600.0f);
+                l = body + burst * unit_noise(seed, 0u, (uint32_t) n);
+                r = 0.8f * l + 0.2f * burst * unit_noise(seed, 1u, (uint32_t) n);
+            }
+        }
+        float* base = audio + (long long) clipLocal * nCh * nSamples + n;
+        base[0] = l;
+        if (nCh > 1)
+            base[nSamples] = r;
+    }
+}
+
+thread_local char g_cudaErr[256];
+long long g_launches = 0;
+
+int check(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess)
+        return 0;
+    snprintf(g_cudaErr, sizeof g_cudaErr, "%s: %s", what, cudaGetErrorString(e));
+    return -1;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* jbk_last_cuda_error(void) { return g_cudaErr; }
+long long jbk_launch_count(void) { return g_launches; }
+
+int jbk_launch_process(const ProcArgs* args, void* stream)
+{
+    if (args->nClips <= 0 || args->nSamples <= 0)
+        return 0;
+    const int grid = (args->nClips + JB_CTA_THREADS - 1) / JB_CTA_THREADS;
+    jb_process_kernel<<<grid, JB_CTA_THREADS, 0, (cudaStream_t) stream>>>(*args);
+    ++g_launches;
+    return check(cudaGetLastError(), "jb_process_kernel launch");
+}
+
+int jbk_launch_fill(float* dst, float value, long long count, void* stream)
+{
+    if (count <= 0)
+        return 0;
+    long long blocks = (count + 255) / 256;
+    if (blocks > 148 * 16)
+        blocks = 148 * 16;
+    jb_fill_kernel<<<(int) blocks, 256, 0, (cudaStream_t) stream>>>(dst, value, count);
+    ++g_launches;
+    return check(cudaGetLastError(), "jb_fill_kernel launch");
+}
+
+int jbk_launch_synth(float* dAudio, int kind, long long firstClip, int nClips, int nCh, int nSamples,
+                     double sampleRate, unsigned int seed, void* stream)
+{
+    if (nClips <= 0 || nSamples <= 0)
+        return 0;
+    jb_synth_kernel<<<148 * 8, 256, 0, (cudaStream_t) stream>>>(dAudio, kind, firstClip, nClips, nCh, nSamples,
+                                                               (float) sampleRate, seed);
+    ++g_launches;
+    return check(cudaGetLastError(), "jb_synth_kernel launch");
+}
+
+} // extern "C"

@@ -1,0 +1,95 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every declared symbol, mirrors the
+reference's parameter surface (ids, ranges, defaults, programs) and refuses to compute without
+a GPU (no CPU fallback).  No compute calls here."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from cases import PLUGINS
+
+
+def test_library_exports_every_declared_symbol(jb):
+    L = jb.lib()
+    names = jb.exported_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(L, name), "include/juicy_batch.h declares %s but the library does not export it" % name
+    assert L.jb_abi_version() == 1
+
+
+@pytest.mark.parametrize("plugin", PLUGINS)
+def test_parameter_surface_matches_oracle(plugin, jb, port):
+    eng = jb.BatchProcessor(plugin, 4, device=-1)
+    ora = port.PortPlugin(plugin)
+    info = eng.parameterInfo()
+    assert [p["id"] for p in info] == ora.param_ids()
+    for i, p in enumerate(info):
+        lo, hi, interval = ora.param_range(i)
+        assert (p["min"], p["max"]) == (lo, hi)
+        assert eng.getRawParameterValue(p["id"]) == ora.get_param(p["id"]), p["id"]
+    assert eng.getNumPrograms() == ora.num_programs()
+    for g in range(eng.getNumPrograms()):
+        eng.setCurrentProgram(g)
+        ora.set_program(g)
+        assert eng.getCurrentProgram() == ora.lib.get_program(ora.h)
+        assert eng.getProgramName(g) == ora.program_name(g)
+        for p in info:
+            assert eng.getRawParameterValue(p["id"]) == ora.get_param(p["id"]), (g, p["id"])
+    # host automation: plain values, out-of-range values (clamped), normalised values
+    for p in info:
+        if p["is_output"]:
+            continue
+        for v in (p["min"] - 1.0, p["min"], 0.3 * p["min"] + 0.7 * p["max"], p["max"], p["max"] + 5.0):
+            eng.setParameter(p["id"], v)
+            ora.set_param(p["id"], v)
+            assert eng.getRawParameterValue(p["id"]) == ora.get_param(p["id"]), (p["id"], v)
+        for n in (0.0, 0.123, 0.5, 0.77, 1.0):
+            eng.setValueNotifyingHost(p["id"], n)
+            ora.set_param_normalised(p["id"], n)
+            assert eng.getRawParameterValue(p["id"]) == ora.get_param(p["id"]), (p["id"], n)
+    eng.close()
+
+
+def test_unknown_ids_and_slots_are_errors(jb):
+    eng = jb.BatchProcessor(["JuicyPunch", "JuicyWidth"], 2, device=-1)
+    with pytest.raises(jb.JuicyBatchError):
+        eng.getRawParameterValue("drive", slot=0)
+    with pytest.raises(jb.JuicyBatchError):
+        eng.setParameter("punch", 1.0, slot=5)
+    assert eng.getRawParameterValue("haasMs", slot="JuicyWidth") == 12.0
+    eng.close()
+    with pytest.raises(jb.JuicyBatchError):
+        jb.BatchProcessor([99], 2, device=-1)
+    with pytest.raises(jb.JuicyBatchError):
+        jb.BatchProcessor("JuicyPunch", 0, device=-1)
+    with pytest.raises(jb.JuicyBatchError):
+        jb.BatchProcessor(["JuicyPunch"] * 9, 1, device=-1)
+
+
+def test_no_cpu_fallback(jb):
+    """Without a device the engine must refuse to render -- never fall back to host code."""
+    eng = jb.BatchProcessor("JuicySaturator", 2, device=-1)
+    with pytest.raises(jb.JuicyBatchError) as e:
+        eng.prepareToPlay(48000.0, 512)
+    assert e.value.code == -3
+    with pytest.raises(jb.JuicyBatchError):
+        eng.processBlock(np.zeros((2, 2, 64), dtype=np.float32))
+    eng.close()
+    if jb.device_count() == 0:
+        with pytest.raises(jb.JuicyBatchError) as e:
+            jb.BatchProcessor("JuicySaturator", 2, device=0)
+        assert e.value.code == -3
+
+
+def test_host_synth_shapes(jb):
+    for kind in ("sweep", "noise", "impulse", "drum", "mixed"):
+        x = jb.synth_clips(kind, 3, 5, 2048)
+        assert x.shape == (5, 2, 2048) and np.isfinite(x).all()
+        assert np.abs(x).max() <= 1.3
+    a = jb.synth_clips("noise", 0, 4, 256)
+    b = jb.synth_clips("noise", 2, 2, 256)
+    assert np.array_equal(a[2:], b), "first_clip must offset the per-clip seeds"
+    m = jb.synth_clips("mixed", 0, 4, 256)
+    for k, kind in enumerate(("sweep", "noise", "impulse", "drum")):
+        assert np.array_equal(m[k], jb.synth_clips(kind, k, 1, 256)[0])
