@@ -34,10 +34,57 @@ __device__ __forceinline__ float jlimitf(float lo, float hi, float v) { return v
 __device__ __forceinline__ float jmap3(float v, float lo, float hi) { return lo + v * (hi - lo); }
 
 // Per-sample transcendentals.  The oracle uses glibc's (nearly correctly rounded)
-// float functions; evaluating in fp64 and rounding once keeps the device within
-// a fraction of an ulp of them where the recurrence is sensitive (Texture-metal
-// cos); the others use CUDA's <=2 ulp float versions.
-__device__ __forceinline__ float cos_exact(float x) { return (float) cos((double) x); }
+// float functions; block-rate pow/log10 are evaluated in fp64 and rounded once,
+// Texture-metal's cos restates glibc's own algorithm (below), the others use
+// CUDA's <= 2 ulp float versions.
+// std::cos(float) as glibc >= 2.28 computes it (sysdeps/ieee754/flt-32/s_cosf.c + sincosf.h,
+// from ARM's optimized-routines): reduce by pi/2 in double, a degree-8 (cos) or degree-7 (sin)
+// polynomial in double, one rounding to float.  Restating the published algorithm with its
+// published coefficients makes the device bit-identical to the oracle's libm for Texture-metal's
+// per-sample pole angle, the one transcendental whose last bit the recurrences amplify
+// (SURVEY.md Appendix D.3).  glibc selects its FMA build on every x86-64 CPU with FMA, hence
+// the explicit fma() here (a double-rounding difference would be ~1e-16 relative anyway).
+__device__ __forceinline__ float cosf_glibc(float y)
+{
+    const double hpiInv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+    const double C0 = 1.0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+                 C4 = 0x1.99343027bf8c3p-16;
+    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+    const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu; // abstop12
+    double x = (double) y;
+    int n = 0;
+    double sg = 1.0; // the second table row is the first with the cosine coefficients negated
+    if (top < 0x3f4u) {                 // |y| < 0.75 (abstop12(pi/4))
+        if (top < 0x398u)               // |y| < 2^-12
+            return 1.0f;
+        n = 1;
+    } else if (top < 0x42fu) {          // |y| < 120
+        const double r = x * hpiInv;
+        const int q = ((int) r + 0x800000) >> 24;
+        x = fma(-(double) q, hpi, x);
+        if (q & 2)
+            sg = -1.0;
+        if (((q + 1) & 2) != 0)         // sign[q & 3] = {1, -1, -1, 1}
+            x = -x;
+        n = q ^ 1;
+    } else {
+        return (float) cos((double) y); // outside the range any caller here produces
+    }
+    const double x2 = x * x;
+    if ((n & 1) == 0) {
+        const double x3 = x * x2;
+        const double s1 = fma(x2, S3, S2);
+        const double x7 = x3 * x2;
+        const double s = fma(x3, S1, x);
+        return (float) fma(x7, s1, s);
+    }
+    const double x4 = x2 * x2;
+    const double c2 = sg * fma(x2, C4, C3);
+    const double c1 = sg * fma(x2, C1, C0);
+    const double x6 = x4 * x2;
+    const double c = fma(x4, sg * C2, c1);
+    return (float) fma(x6, c2, c);
+}
 __device__ __forceinline__ float pow_exact(float x, float y) { return (float) pow((double) x, (double) y); }
 __device__ __forceinline__ float log10_exact(float x) { return (float) log10((double) x); }
 
@@ -496,7 +543,7 @@ struct MainTexture : MainBase {
     {
         const float f = jlimitf(20.0f, c->fMax, c->modeF[k] * bend);
         const float theta = 2.0f * PI_F * f / c->srf;
-        return c->modeTwoR[k] * cos_exact(theta);
+        return c->modeTwoR[k] * cosf_glibc(theta);
     }
     // waveguideRead (:91-105) on the time-major ring of this channel
     __device__ __forceinline__ float waveRead(const float* line) const

@@ -107,10 +107,13 @@ def test_state_carries_across_calls_and_reset(jb, port):
     eng = jb.BatchProcessor(chain, 8)
     eng.prepareToPlay(SAMPLE_RATE, BLOCK)
     whole = eng.processBlock(clips)
-    eng.reset()
-    first = eng.processBlock(clips[:, :, :BLOCK])
-    second = eng.processBlock(clips[:, :, BLOCK:])
+    split = jb.BatchProcessor(chain, 8)  # a fresh set of instances (Motion's LCG survives prepareToPlay)
+    split.prepareToPlay(SAMPLE_RATE, BLOCK)
+    first = split.processBlock(clips[:, :, :BLOCK])
+    second = split.processBlock(clips[:, :, BLOCK:])
     assert np.array_equal(np.concatenate([first, second], axis=2), whole)
+    assert np.array_equal(split.getLatestMetrics(6), eng.getLatestMetrics(6))
+    split.close()
     eng.prepareToPlay(SAMPLE_RATE, BLOCK)
     again = eng.processBlock(clips)
     # Motion's LCG is seeded at construction only (JuicyMotion/PluginProcessor.h:65), so a second
