@@ -160,6 +160,19 @@ int jb_synth_fill(float* d_audio, int kind, long long first_clip, int n_clips, i
 int jb_synth_fill_host(float* h_audio, int kind, long long first_clip, int n_clips, int n_channels,
                        int n_samples, double sample_rate, unsigned int seed);
 
+/* Render-kernel choice.  The library has two sm_100a kernels for processBlock: one lane per clip
+ * (any chain; fills the GPU from ~75k clips up) and a block-cooperative, time-parallel one (chains of
+ * Punch-first / Width / Infer, host block <= 512, 16-byte aligned audio) for smaller batches.
+ * mode JB_PATH_AUTO picks per call; JB_PATH_LANE / JB_PATH_COOP force one (COOP fails with
+ * JB_ERR_UNSUPPORTED when the chain or call shape is outside its scope).  Both produce the same
+ * samples; their records agree to rounding (the cooperative one tree-reduces analyze()'s plain sums). */
+#define JB_PATH_AUTO 0
+#define JB_PATH_LANE 1
+#define JB_PATH_COOP 2
+int jb_set_path(jb_engine* e, int mode);
+/* Launches of each render kernel by this engine so far (either pointer may be null). */
+int jb_path_launches(const jb_engine* e, long long* cooperative, long long* lane_per_clip);
+
 /* Number of kernel launches issued by this library since load (bench evidence). */
 long long jb_launch_count(void);
 /* Device time spent in the render kernel since the previous call of this function:

@@ -1,0 +1,677 @@
+// jb_coop.cu -- block-cooperative, time-parallel render kernel for sm_100a.
+//
+// The lane-per-clip kernel (jb_kernels.cu) needs tens of thousands of clips to fill a B200.
+// This kernel is for batches that do not offer that: one persistent CTA per SM owns up to
+// CO_GMAX clips and walks them through time in steps of CO_T samples, with warp roles
+//
+//   producer  : 1-D bulk async copies (cp.async.bulk + mbarrier) global -> shared tile and back;
+//   scouts    : one lane per (clip, channel) row runs the CHEAP exact recurrences of the next
+//               step sequentially (JuicyPunch's fast/slow envelopes) and drops a checkpoint of the
+//               state every CO_CH samples;
+//   bulk      : one warp per clip-step, one lane per CO_CH-sample chunk: restarts the recurrence
+//               from the scout's checkpoint (bit-identical, same operand order) and does the
+//               expensive pointwise work (pow, tanh, mid/side, gains) for all chunks in parallel,
+//               plus the order-independent sums of the analyzer (tree-reduced);
+//   analyzers : one lane per (clip, plugin) walks JuicinessAnalyzer's nonlinear state machine
+//               (attack/release envelopes, onset cooldown, band splits) strictly in sample order,
+//               one host block behind the bulk warps, reading the mono sums the bulk warps left
+//               in an L2-resident scratch ring.
+//
+// What is exact and what is reassociated: every recurrence that feeds a discontinuity or a
+// singular function (analyzer envelopes -> onset threshold, Punch envelopes -> pow at 0, Width's
+// in-block width decay) is evaluated with the reference's own fp32 operation order; only the plain
+// sums of analyze() (rms, side, corr, getRMSLevel) are tree-reduced, and per-sample pow/tanh use
+// MUFU-based evaluations accurate to ~1e-6 relative (the tests hold 1e-5 of clip peak).
+//
+// Reference lines are cited per routine, relative to /root/reference.
+#include "jb_device.cuh"
+
+#include <stdint.h>
+#include <stdio.h>
+
+namespace {
+
+using namespace jbdev;
+
+constexpr int CO_T = 256;            // samples per step
+constexpr int CO_CH = 8;             // samples per bulk lane per step (32 lanes x 8 = CO_T)
+constexpr int CO_GMAX = 32;          // clips per CTA group
+constexpr int CO_ROWS = 2 * CO_GMAX; // (clip, channel) rows of a tile
+constexpr int CO_PITCH = CO_T + 4;   // floats per tile row (+16 B: row-walking lanes hit distinct banks)
+constexpr int CO_BLOCKMAX = 512;     // largest host block size this path takes
+constexpr int CO_MAXCHAIN = 3;       // plugins per chain on this path
+constexpr int CO_NSIG = CO_MAXCHAIN + 1;
+constexpr int CO_W_PRODUCER = 0;
+constexpr int CO_W_SCOUT = 1, CO_NSCOUT = CO_ROWS / 32;                      // 2 warps
+constexpr int CO_W_ANA = CO_W_SCOUT + CO_NSCOUT, CO_NANA = CO_GMAX * CO_MAXCHAIN / 32; // 3 warps
+constexpr int CO_W_BULK = CO_W_ANA + CO_NANA, CO_NBULK = 14;
+constexpr int CO_WARPS = CO_W_BULK + CO_NBULK;                               // 20
+constexpr int CO_THREADS = CO_WARPS * 32;                                    // 640
+
+struct CoopSmem {
+    float tile[2][CO_ROWS][CO_PITCH];           // 133,120 B
+    float2 ckpt[2][CO_ROWS][CO_T / CO_CH];      //  32,768 B  Punch (fast, slow) at every chunk start
+    float stats[2][CO_GMAX][CO_NSIG][8];        //   8,192 B  rms, peak, side, corr, l2, r2 per (block parity, clip, signal)
+    float widthTab[CO_BLOCKMAX + 1];            //   width * dyn^k, k multiplies applied in sample order
+    int widthPos[CO_GMAX];                      //   ring write position of the step's first sample
+    int widthCount[CO_GMAX];                    //   multiplies so far in the current host block
+    unsigned long long bar[2];                  //   mbarriers: tile slot filled
+};
+
+// ---------------------------------------------------------------- PTX wrappers (async proxy)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_load(void* smemDst, const void* gmemSrc, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smemDst)),
+                 "l"(gmemSrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmemDst, const void* smemSrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmemDst), "r"(smem_u32(smemSrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- pointwise math of the bulk lanes
+// std::pow(t, e) for t >= 0, 0 < e < 1 (JuicyPunch/PluginProcessor.cpp:100): 2^(e * log2 t) on the
+// MUFU unit.  |rel err| <~ 3e-6 at the smallest t that still matters.
+__device__ __forceinline__ float pow_unit(float t, float e)
+{
+    const float r = exp2f(e * __log2f(t)); // log2(0) = -inf -> 2^-inf = 0
+    return r;
+}
+// std::tanh: odd minimax polynomial below 0.55 (rel err 8e-8), 1 - 2/(e^{2|x|} + 1) above.
+__device__ __forceinline__ float tanh_fast(float x)
+{
+    const float ax = fabsf(x);
+    const float x2 = x * x;
+    float p = -0x1.825866p-8f;
+    p = fmaf(p, x2, 0x1.54b8a4p-6f);
+    p = fmaf(p, x2, -0x1.b898dep-5f);
+    p = fmaf(p, x2, 0x1.1109aep-3f);
+    p = fmaf(p, x2, -0x1.55553ep-2f);
+    const float small = fmaf(x * x2, p, x);
+    const float e = exp2f(ax * 2.885390081777927f); // e^{2|x|}; inf for large |x| -> 1
+    const float big = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+    return ax < 0.55f ? small : big;
+}
+
+// ---------------------------------------------------------------- time cursor over the call's steps
+struct Cursor {
+    int blk, off, pos, n, nBlk; // host block, offset inside it, absolute sample, step length, block length
+    bool valid;
+};
+__device__ __forceinline__ Cursor cursor_at(const ProcArgs& a, int blk, int off)
+{
+    Cursor c;
+    c.blk = blk;
+    c.off = off;
+    c.pos = blk * a.blockSize + off;
+    c.valid = c.pos < a.nSamples;
+    c.nBlk = min(a.blockSize, a.nSamples - blk * a.blockSize);
+    c.n = c.valid ? min(CO_T, c.nBlk - off) : 0;
+    return c;
+}
+__device__ __forceinline__ Cursor cursor_next(const ProcArgs& a, const Cursor& c)
+{
+    if (c.off + c.n < c.nBlk)
+        return cursor_at(a, c.blk, c.off + c.n);
+    return cursor_at(a, c.blk + 1, 0);
+}
+
+// ---------------------------------------------------------------- bulk: per-plugin chunk transforms
+
+// JuicyPunch/PluginProcessor.cpp:94-110 on one channel's chunk, restarting the two linear
+// envelopes from the scout's checkpoint (same operand order as the scout => same bits).
+__device__ __forceinline__ void punch_chunk(float (&x)[CO_CH], float2 ck, const PunchCoef& c)
+{
+    float fEnv = ck.x, sEnv = ck.y;
+    const float invTanhDrive = 1.0f / c.tanhDrive;
+#pragma unroll
+    for (int i = 0; i < CO_CH; ++i) {
+        const float dry = x[i];
+        const float adry = fabsf(dry);
+        fEnv = c.omFast * adry + c.fastCoeff * fEnv;
+        sEnv = c.omSlow * adry + c.slowCoeff * sEnv;
+        const float transient = jmaxf(0.0f, fEnv - sEnv);
+        const float transientCurve = pow_unit(transient, c.curveExp);
+        const float punchGain = 1.0f + c.punchK * transientCurve;
+        const float sustainGain = 1.0f + c.sustainK * jmaxf(0.0f, sEnv - transient * 0.6f);
+        float wet = dry * punchGain * sustainGain;
+        const float soft = tanh_fast(wet * c.drive) * invTanhDrive;
+        const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
+        wet = soft + c.clipAmt * (hard - soft);
+        x[i] = (dry + c.mix * (wet - dry)) * c.outGain;
+    }
+}
+
+// JuicyWidth/PluginProcessor.cpp:106-137 on one clip's chunk.  width after k in-block multiplies
+// comes from the table (bit-identical to the reference's repeated `width *= dynamicLimit`);
+// the right channel's wet signal goes through the 60 ms ring in global memory (clip-major).
+__device__ __forceinline__ void width_chunk(float (&l)[CO_CH], float (&r)[CO_CH], const WidthCoef& c, const float* tab,
+                                            int kStart, int& warpTotal, float* ring, int wpos0, int lane, int nValid)
+{
+    int kk[CO_CH];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < CO_CH; ++i) {
+        const float corrProxy = jlimitf(-1.0f, 1.0f, l[i] * r[i] * 12.0f);
+        cnt += (corrProxy < -0.1f) ? 1 : 0;
+        kk[i] = cnt;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += t;
+    }
+    warpTotal = __shfl_sync(0xffffffffu, incl, 31);
+    const int base = kStart + incl - cnt;
+
+    float wetL[CO_CH];
+    int wp = wpos0 + lane * CO_CH;
+    wp -= wp >= c.ringLen ? c.ringLen : 0; // wpos0 < ringLen and lane*CO_CH < CO_T <= ringLen
+#pragma unroll
+    for (int i = 0; i < CO_CH; ++i) {
+        const float width = tab[base + kk[i]];
+        const float mid = 0.5f * (l[i] + r[i]);
+        const float side = 0.5f * (l[i] - r[i]) * (1.0f + width);
+        wetL[i] = mid + side;
+        const float wetR = mid - side;
+        int p = wp + i;
+        p -= p >= c.ringLen ? c.ringLen : 0;
+        if (i < nValid)
+            ring[p] = wetR;
+    }
+    __syncwarp(); // the delayed read below may land on a value another lane wrote in this step
+#pragma unroll
+    for (int i = 0; i < CO_CH; ++i) {
+        int p = wp + i;
+        p -= p >= c.ringLen ? c.ringLen : 0;
+        int rp = p - c.delaySamples;
+        rp += rp < 0 ? c.ringLen : 0;
+        const float wetR = (i < nValid) ? __ldcg(ring + rp) : 0.0f;
+        const float dryL = l[i], dryR = r[i];
+        l[i] = (dryL + c.mix * (wetL[i] - dryL)) * c.outGain;
+        r[i] = (dryR + c.mix * (wetR - dryR)) * c.outGain;
+    }
+}
+
+// JuicyInfer/PluginProcessor.cpp:79: buffer.applyGain(trimGain)
+__device__ __forceinline__ void infer_chunk(float (&l)[CO_CH], float (&r)[CO_CH], const InferCoef& c)
+{
+    if (c.gainMode == 1) {
+#pragma unroll
+        for (int i = 0; i < CO_CH; ++i) {
+            l[i] *= c.trimGain;
+            r[i] *= c.trimGain;
+        }
+    } else if (c.gainMode == 2) {
+#pragma unroll
+        for (int i = 0; i < CO_CH; ++i) {
+            l[i] = 0.0f;
+            r[i] = 0.0f;
+        }
+    }
+}
+
+// Samples past the end of a (ragged) step carry nothing into sums, rings or later stages.
+__device__ __forceinline__ void mask_chunk(float (&l)[CO_CH], float (&r)[CO_CH], int nValid)
+{
+#pragma unroll
+    for (int i = 0; i < CO_CH; ++i) {
+        if (i >= nValid) {
+            l[i] = 0.0f;
+            r[i] = 0.0f;
+        }
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
+// The order-independent sums of analyze() over this lane's chunk of one signal
+// (JuicinessAnalyzer.cpp:76-77,86-91,105-106), tree-reduced over the warp and added to the
+// block's running totals; the mono sum of every sample goes to the analyzer lanes' scratch ring.
+__device__ __forceinline__ void signal_stats(const float (&l)[CO_CH], const float (&r)[CO_CH], float* acc, bool firstStep,
+                                             float* monoDst, int lane, int nValid)
+{
+    float mono[CO_CH];
+    float rms = 0.0f, peak = 0.0f, side = 0.0f, corr = 0.0f, l2 = 0.0f, r2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < CO_CH; ++i) {
+        const float m = 0.5f * (l[i] + r[i]);
+        mono[i] = m;
+        rms = fmaf(m, m, rms);
+        peak = fmaxf(peak, fabsf(m));
+        const float s = 0.5f * (l[i] - r[i]);
+        side = fmaf(s, s, side);
+        corr = fmaf(l[i], r[i], corr);
+        l2 = fmaf(l[i], l[i], l2);
+        r2 = fmaf(r[i], r[i], r2);
+    }
+    if (nValid > 0)
+        __stcg(reinterpret_cast<float4*>(monoDst), make_float4(mono[0], mono[1], mono[2], mono[3]));
+    if (nValid > 4)
+        __stcg(reinterpret_cast<float4*>(monoDst) + 1, make_float4(mono[4], mono[5], mono[6], mono[7]));
+    rms = warp_sum(rms);
+    peak = warp_max(peak);
+    side = warp_sum(side);
+    corr = warp_sum(corr);
+    l2 = warp_sum(l2);
+    r2 = warp_sum(r2);
+    if (lane == 0) {
+        if (firstStep) {
+            acc[0] = rms; acc[1] = peak; acc[2] = side; acc[3] = corr; acc[4] = l2; acc[5] = r2;
+        } else {
+            acc[0] += rms; acc[1] = fmaxf(acc[1], peak); acc[2] += side; acc[3] += corr; acc[4] += l2; acc[5] += r2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- analyzer lanes
+__device__ __forceinline__ void ana_walk(AnaState& st, AnaAcc& acc, const float* stream, int n, const AnaCoef& c)
+{
+    const float4* p = reinterpret_cast<const float4*>(stream);
+    const int n4 = n >> 2; // the path requires n % 4 == 0
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+    if (0 < n4) q0 = __ldcg(p + 0);
+    if (1 < n4) q1 = __ldcg(p + 1);
+    if (2 < n4) q2 = __ldcg(p + 2);
+    if (3 < n4) q3 = __ldcg(p + 3);
+    for (int q = 0; q < n4; ++q) {
+        const float4 cur = q0;
+        q0 = q1; q1 = q2; q2 = q3;
+        if (q + 4 < n4)
+            q3 = __ldcg(p + q + 4);
+        ana_step(st, acc, cur.x, c);
+        ana_step(st, acc, cur.y, c);
+        ana_step(st, acc, cur.z, c);
+        ana_step(st, acc, cur.w, c);
+    }
+}
+
+__device__ __forceinline__ StatSums load_stats(const float* s)
+{
+    StatSums t;
+    t.rms = s[0]; t.peak = s[1]; t.side = s[2]; t.corr = s[3];
+    t.l2 = (double) s[4]; t.r2 = (double) s[5];
+    return t;
+}
+
+struct CoopArgs {
+    ProcArgs p;
+    float* monoScratch; // [grid][CO_GMAX][chainLen + 1][2][CO_BLOCKMAX]
+    int groupClips;     // clips per group (<= CO_GMAX)
+    int numGroups;
+};
+
+__global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_constant__ CoopArgs ca)
+{
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    CoopSmem& sm = *reinterpret_cast<CoopSmem*>(smemRaw);
+    const ProcArgs& a = ca.p;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = a.chainLen;
+    const int nSig = L + 1;
+    const AnaCoef ana = a.ana;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // which slot (if any) is Width; Punch may only lead the chain (its scout reads the raw input)
+    int widthSlot = -1;
+    for (int s = 0; s < L; ++s)
+        if (a.slot[s].kind == K_WIDTH)
+            widthSlot = s;
+    const bool punchFirst = a.slot[0].kind == K_PUNCH;
+    if (widthSlot >= 0 && threadIdx.x == 32) { // width after k multiplies, in the reference's order (:93,:112)
+        const WidthCoef& w = a.slot[widthSlot].c.width;
+        float v = w.width;
+        sm.widthTab[0] = v;
+        for (int k = 1; k <= CO_BLOCKMAX; ++k) {
+            v *= w.dynamicLimit;
+            sm.widthTab[k] = v;
+        }
+    }
+    __syncthreads();
+
+    unsigned gstep = 0; // steps loaded so far by this CTA (tile slot = gstep & 1, mbarrier parity = (gstep >> 1) & 1)
+    float* const monoCta = ca.monoScratch + (size_t) blockIdx.x * CO_GMAX * nSig * 2 * CO_BLOCKMAX;
+
+    for (int group = blockIdx.x; group < ca.numGroups; group += gridDim.x) {
+        const int clip0 = group * ca.groupClips;
+        const int G = min(ca.groupClips, a.nClips - clip0);
+        const int rows = 2 * G;
+
+        // ---- per-role state for this group
+        // scout: Punch envelopes of row (clip, ch)
+        float scF = 0.0f, scS = 0.0f;
+        const int scRow = (warp - CO_W_SCOUT) * 32 + lane;
+        const bool isScout = warp >= CO_W_SCOUT && warp < CO_W_SCOUT + CO_NSCOUT && punchFirst && scRow < rows;
+        if (isScout) {
+            const long long clip = clip0 + (scRow >> 1);
+            const int b = a.slot[0].stateBase + AV_COUNT;
+            scF = a.state[(long long) (b + PV_FAST0 + (scRow & 1)) * a.clipPitch + clip];
+            scS = a.state[(long long) (b + PV_SLOW0 + (scRow & 1)) * a.clipPitch + clip];
+        }
+        // analyzer: lane <-> (plugin slot, clip)
+        const int anaIdx = (warp - CO_W_ANA) * 32 + lane;
+        const int anaSlot = anaIdx / CO_GMAX, anaClip = anaIdx % CO_GMAX;
+        const bool isAna = warp >= CO_W_ANA && warp < CO_W_ANA + CO_NANA && anaSlot < L && anaClip < G;
+        AnaState ast {};
+        float preScore = 0.0f;
+        if (isAna) {
+            const long long clip = clip0 + anaClip;
+            const int b = a.slot[anaSlot].stateBase;
+            auto ld = [&](int v) { return a.state[(long long) (b + v) * a.clipPitch + clip]; };
+            ast.sEnv = ld(AV_SHORT); ast.lEnv = ld(AV_LONG); ast.low = ld(AV_LOW); ast.high = ld(AV_HIGH);
+            ast.repEma = ld(AV_REP_EMA); ast.fatEma = ld(AV_FAT_EMA);
+            ast.cool = __float_as_int(ld(AV_COOLDOWN));
+            preScore = ld(AV_PRE_SCORE);
+        }
+        if (widthSlot >= 0 && threadIdx.x < G) {
+            const int b = a.slot[widthSlot].stateBase + AV_COUNT;
+            sm.widthPos[threadIdx.x] = __float_as_int(a.state[(long long) (b + WV_WPOS) * a.clipPitch + clip0 + threadIdx.x]);
+            sm.widthCount[threadIdx.x] = 0;
+        }
+
+        // ---- prologue: load step 0 and scout it
+        Cursor cur = cursor_at(a, 0, 0);
+        auto issue_load = [&](const Cursor& c, unsigned step) {
+            // producer warp: one bulk copy per (clip, channel) row
+            const int slot = step & 1;
+            if (lane == 0)
+                mbar_expect_tx(&sm.bar[slot], (uint32_t) (rows * c.n * 4));
+            __syncwarp();
+            for (int row = lane; row < rows; row += 32) {
+                const float* src = a.in + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.nSamples + c.pos;
+                bulk_load(&sm.tile[slot][row][0], src, (uint32_t) (c.n * 4), &sm.bar[slot]);
+            }
+        };
+        auto scout_step = [&](const Cursor& c, unsigned step) {
+            const int slot = step & 1;
+            mbar_wait(&sm.bar[slot], (step >> 1) & 1);
+            if (!isScout)
+                return;
+            const PunchCoef& pc = a.slot[0].c.punch;
+            const float4* src = reinterpret_cast<const float4*>(&sm.tile[slot][scRow][0]);
+            float2* ck = &sm.ckpt[slot][scRow][0];
+            for (int i = 0; i < c.n; i += CO_CH) {
+                ck[i / CO_CH] = make_float2(scF, scS);
+                const float4 v0 = src[i / 4], v1 = src[i / 4 + 1];
+                const float x[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+#pragma unroll
+                for (int k = 0; k < CO_CH; ++k) {
+                    if (i + k < c.n) { // JuicyPunch/PluginProcessor.cpp:94-96
+                        const float adry = fabsf(x[k]);
+                        scF = pc.omFast * adry + pc.fastCoeff * scF;
+                        scS = pc.omSlow * adry + pc.slowCoeff * scS;
+                    }
+                }
+            }
+        };
+        __syncthreads(); // widthPos/widthCount visible; previous group's tiles are drained
+        if (warp == CO_W_PRODUCER) {
+            bulk_wait_read();
+            issue_load(cur, gstep);
+        }
+        if (warp >= CO_W_SCOUT && warp < CO_W_SCOUT + CO_NSCOUT)
+            scout_step(cur, gstep);
+        __syncthreads();
+
+        // ---- main loop over steps
+        while (cur.valid) {
+            const Cursor nxt = cursor_next(a, cur);
+            const unsigned step = gstep, slot = gstep & 1;
+            const int blockPar = cur.blk & 1;
+
+            if (warp == CO_W_PRODUCER) {
+                if (nxt.valid) {
+                    bulk_wait_read(); // the store that last read the other slot has drained
+                    issue_load(nxt, step + 1);
+                }
+            } else if (warp < CO_W_SCOUT + CO_NSCOUT) {
+                if (nxt.valid)
+                    scout_step(nxt, step + 1);
+            } else if (warp < CO_W_ANA + CO_NANA) {
+                // analyzers run one host block behind: pre-analysis of block blk-1 during the first
+                // step of block blk, post-analysis during the second (or both, if blk is one step long)
+                if (isAna && cur.blk > 0) {
+                    const int pb = cur.blk - 1, ppar = pb & 1, pn = a.blockSize;
+                    const bool single = cur.nBlk <= CO_T;
+                    const float* streams = monoCta + ((size_t) anaClip * nSig) * 2 * CO_BLOCKMAX + ppar * CO_BLOCKMAX;
+                    if (cur.off == 0) { // analyze(buffer) before the plugin's DSP (e.g. JuicyPunch/PluginProcessor.cpp:82)
+                        AnaAcc acc;
+                        ana_walk(ast, acc, streams + (size_t) anaSlot * 2 * CO_BLOCKMAX, pn, ana);
+                        preScore = ana_finish(ast, acc, load_stats(sm.stats[ppar][anaClip][anaSlot]), pn, ana).score;
+                    }
+                    if (single || cur.off == CO_T) { // analyze(buffer) after it (:114)
+                        AnaAcc acc;
+                        ana_walk(ast, acc, streams + (size_t) (anaSlot + 1) * 2 * CO_BLOCKMAX, pn, ana);
+                        const Metrics m = ana_finish(ast, acc, load_stats(sm.stats[ppar][anaClip][anaSlot + 1]), pn, ana);
+                        publish_record(a, anaSlot, clip0 + anaClip, a.histFirstBlock + pb, m, preScore, 0.0f);
+                    }
+                }
+            } else {
+                // ---- bulk warps
+                mbar_wait(&sm.bar[slot], (step >> 1) & 1);
+                const int nValid = max(0, min(CO_CH, cur.n - lane * CO_CH));
+                const bool firstStep = cur.off == 0;
+                for (int ci = warp - CO_W_BULK; ci < G; ci += CO_NBULK) {
+                    float* rowL = &sm.tile[slot][2 * ci][lane * CO_CH];
+                    float* rowR = &sm.tile[slot][2 * ci + 1][lane * CO_CH];
+                    float l[CO_CH], r[CO_CH];
+                    {
+                        const float4 a0 = *reinterpret_cast<const float4*>(rowL), a1 = *reinterpret_cast<const float4*>(rowL + 4);
+                        const float4 b0 = *reinterpret_cast<const float4*>(rowR), b1 = *reinterpret_cast<const float4*>(rowR + 4);
+                        l[0] = a0.x; l[1] = a0.y; l[2] = a0.z; l[3] = a0.w; l[4] = a1.x; l[5] = a1.y; l[6] = a1.z; l[7] = a1.w;
+                        r[0] = b0.x; r[1] = b0.y; r[2] = b0.z; r[3] = b0.w; r[4] = b1.x; r[5] = b1.y; r[6] = b1.z; r[7] = b1.w;
+                    }
+                    mask_chunk(l, r, nValid);
+                    float* monoClip = monoCta + ((size_t) ci * nSig) * 2 * CO_BLOCKMAX + blockPar * CO_BLOCKMAX + cur.off + lane * CO_CH;
+                    signal_stats(l, r, sm.stats[blockPar][ci][0], firstStep, monoClip, lane, nValid);
+                    for (int s = 0; s < L; ++s) {
+                        const SlotDesc& d = a.slot[s];
+                        if (d.kind == K_PUNCH) {
+                            const float2 zero = make_float2(0.0f, 0.0f); // lanes past the step's end have no checkpoint
+                            punch_chunk(l, nValid > 0 ? sm.ckpt[slot][2 * ci][lane] : zero, d.c.punch);
+                            punch_chunk(r, nValid > 0 ? sm.ckpt[slot][2 * ci + 1][lane] : zero, d.c.punch);
+                        } else if (d.kind == K_WIDTH) {
+                            int total = 0;
+                            const int kStart = firstStep ? 0 : sm.widthCount[ci];
+                            const int wpos0 = sm.widthPos[ci];
+                            __syncwarp();
+                            float* ring = a.widthRing + (long long) (clip0 + ci) * a.ringClipStride;
+                            width_chunk(l, r, d.c.width, sm.widthTab, kStart, total, ring, wpos0, lane, nValid);
+                            if (lane == 0) {
+                                sm.widthCount[ci] = kStart + total;
+                                int np = wpos0 + cur.n;
+                                np -= np >= d.c.width.ringLen ? d.c.width.ringLen : 0;
+                                sm.widthPos[ci] = np;
+                            }
+                        } else if (d.kind == K_INFER) {
+                            infer_chunk(l, r, d.c.infer);
+                        }
+                        mask_chunk(l, r, nValid);
+                        signal_stats(l, r, sm.stats[blockPar][ci][s + 1], firstStep, monoClip + (size_t) (s + 1) * 2 * CO_BLOCKMAX,
+                                     lane, nValid);
+                    }
+                    *reinterpret_cast<float4*>(rowL) = make_float4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<float4*>(rowL + 4) = make_float4(l[4], l[5], l[6], l[7]);
+                    *reinterpret_cast<float4*>(rowR) = make_float4(r[0], r[1], r[2], r[3]);
+                    *reinterpret_cast<float4*>(rowR + 4) = make_float4(r[4], r[5], r[6], r[7]);
+                }
+                fence_async_smem(); // tile writes -> visible to the bulk store issued after the barrier
+            }
+            __syncthreads();
+            if (warp == CO_W_PRODUCER) {
+                for (int row = lane; row < rows; row += 32) {
+                    float* dst = a.out + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.nSamples + cur.pos;
+                    bulk_store(dst, &sm.tile[slot][row][0], (uint32_t) (cur.n * 4));
+                }
+                bulk_commit();
+            }
+            ++gstep;
+            cur = nxt;
+        }
+
+        // ---- epilogue: analyzers finish the last host block; everyone stores state
+        const int lastBlk = (a.nSamples + a.blockSize - 1) / a.blockSize - 1;
+        if (isAna) {
+            const int ppar = lastBlk & 1, pn = a.nSamples - lastBlk * a.blockSize;
+            const float* streams = monoCta + ((size_t) anaClip * nSig) * 2 * CO_BLOCKMAX + ppar * CO_BLOCKMAX;
+            {
+                AnaAcc acc;
+                ana_walk(ast, acc, streams + (size_t) anaSlot * 2 * CO_BLOCKMAX, pn, ana);
+                preScore = ana_finish(ast, acc, load_stats(sm.stats[ppar][anaClip][anaSlot]), pn, ana).score;
+            }
+            {
+                AnaAcc acc;
+                ana_walk(ast, acc, streams + (size_t) (anaSlot + 1) * 2 * CO_BLOCKMAX, pn, ana);
+                const Metrics m = ana_finish(ast, acc, load_stats(sm.stats[ppar][anaClip][anaSlot + 1]), pn, ana);
+                publish_record(a, anaSlot, clip0 + anaClip, a.histFirstBlock + lastBlk, m, preScore, 0.0f);
+            }
+            const long long clip = clip0 + anaClip;
+            const int b = a.slot[anaSlot].stateBase;
+            auto stv = [&](int v, float x) { a.state[(long long) (b + v) * a.clipPitch + clip] = x; };
+            stv(AV_SHORT, ast.sEnv); stv(AV_LONG, ast.lEnv); stv(AV_LOW, ast.low); stv(AV_HIGH, ast.high);
+            stv(AV_REP_EMA, ast.repEma); stv(AV_FAT_EMA, ast.fatEma);
+            stv(AV_COOLDOWN, __int_as_float(ast.cool));
+            stv(AV_PRE_SCORE, preScore);
+        }
+        if (isScout) {
+            const long long clip = clip0 + (scRow >> 1);
+            const int b = a.slot[0].stateBase + AV_COUNT;
+            a.state[(long long) (b + PV_FAST0 + (scRow & 1)) * a.clipPitch + clip] = scF;
+            a.state[(long long) (b + PV_SLOW0 + (scRow & 1)) * a.clipPitch + clip] = scS;
+        }
+        __syncthreads(); // analyzers are done with stats/scratch of this group; widthPos is final
+        if (widthSlot >= 0 && threadIdx.x < G) {
+            const int b = a.slot[widthSlot].stateBase + AV_COUNT;
+            a.state[(long long) (b + WV_WPOS) * a.clipPitch + clip0 + threadIdx.x] = __int_as_float(sm.widthPos[threadIdx.x]);
+        }
+    }
+    if (warp == CO_W_PRODUCER)
+        bulk_wait_all();
+}
+
+thread_local char g_coopErr[256];
+
+} // namespace
+
+extern "C" {
+
+const char* jbk_coop_last_error(void) { return g_coopErr; }
+
+// Scratch the coop kernel needs (mono rings of the analyzer lanes), sized for a full grid.
+size_t jbk_coop_scratch_bytes(int chainLen, int numSMs)
+{
+    return sizeof(float) * (size_t) numSMs * CO_GMAX * (size_t) (chainLen + 1) * 2 * CO_BLOCKMAX;
+}
+
+// Can this call take the cooperative path?  (Chain made of Punch / Width / Infer with Punch only
+// in front, host block <= 512, everything 16-byte aligned, the Width ring long enough for a step.)
+int jbk_coop_supported(const ProcArgs* a)
+{
+    if (a->chainLen < 1 || a->chainLen > CO_MAXCHAIN || a->nCh != 2)
+        return 0;
+    if (a->blockSize > CO_BLOCKMAX || a->blockSize % 4 != 0 || a->nSamples % 4 != 0)
+        return 0;
+    if (((uintptr_t) a->in | (uintptr_t) a->out) & 15u)
+        return 0;
+    for (int s = 0; s < a->chainLen; ++s) {
+        const int k = a->slot[s].kind;
+        if (k == K_PUNCH) {
+            if (s != 0)
+                return 0;
+        } else if (k == K_WIDTH) {
+            const WidthCoef& w = a->slot[s].c.width;
+            if (a->ringTimeStride != 1 || w.ringLen - w.delaySamples < CO_T || w.ringLen < CO_T)
+                return 0;
+        } else if (k != K_INFER) {
+            return 0;
+        }
+    }
+    return 1;
+}
+
+int jbk_launch_coop(const ProcArgs* args, float* monoScratch, int numSMs, void* stream)
+{
+    if (args->nClips <= 0 || args->nSamples <= 0)
+        return 0;
+    {
+        cudaError_t e = cudaFuncSetAttribute(jb_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CoopSmem));
+        if (e != cudaSuccess) {
+            snprintf(g_coopErr, sizeof g_coopErr, "cudaFuncSetAttribute(jb_coop_kernel): %s", cudaGetErrorString(e));
+            return -1;
+        }
+    }
+    CoopArgs ca;
+    ca.p = *args;
+    ca.monoScratch = monoScratch;
+    int g = (args->nClips + numSMs - 1) / numSMs;
+    if (g > CO_GMAX)
+        g = CO_GMAX;
+    ca.groupClips = g;
+    ca.numGroups = (args->nClips + g - 1) / g;
+    const int grid = ca.numGroups < numSMs ? ca.numGroups : numSMs;
+    jb_coop_kernel<<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
+    jbk_note_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_coopErr, sizeof g_coopErr, "jb_coop_kernel launch: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -61,6 +61,9 @@ struct VarInit {
     bool everyPrepare; // false: set when the instance is constructed only
 };
 
+// With at least this many clips in a launch, one lane per clip fills the GPU on its own.
+constexpr int kLaneKernelMinClips = 148 * 4 * 32 * 4;
+
 float bitsToFloat(uint32_t u)
 {
     float f;
@@ -88,6 +91,12 @@ struct jb_engine {
     float* dHist = nullptr;
     float* dRing = nullptr;
     float* dWave = nullptr;
+    float* dCoopScratch = nullptr; // mono rings of the cooperative kernel's analyzer lanes
+    bool ringClipMajor = false;    // Width ring layout: [clip][ringLen] (cooperative-capable chains) or [ringLen][clip]
+    bool coopCapable = false;      // chain made of plugins the cooperative kernel implements
+    int numSMs = 0;
+    int pathMode = 0;              // 0 auto, 1 force lane-per-clip, 2 force cooperative (fails if unsupported)
+    long long coopLaunches = 0, laneLaunches = 0;
     int ringLen = 0, waveLen = 0;
     int histMaxBlocks = 0;
     bool stateConstructed = false;
@@ -145,7 +154,8 @@ void freeDevice(jb_engine* e)
     cudaFree(e->dHist);
     cudaFree(e->dRing);
     cudaFree(e->dWave);
-    e->dState = e->dLatest = e->dHist = e->dRing = e->dWave = nullptr;
+    cudaFree(e->dCoopScratch);
+    e->dState = e->dLatest = e->dHist = e->dRing = e->dWave = e->dCoopScratch = nullptr;
     for (int i = 0; i < 3; ++i) {
         cudaFree(e->dStage[i]);
         e->dStage[i] = nullptr;
@@ -261,7 +271,9 @@ int buildArgs(jb_engine* e, ProcArgs& a, const float* dIn, float* dOut, int nSam
     a.state = e->dState + clipOffset;
     a.latest = e->dLatest + clipOffset;
     a.hist = e->dHist ? e->dHist + clipOffset : nullptr;
-    a.widthRing = e->dRing ? e->dRing + clipOffset : nullptr;
+    a.ringClipStride = e->ringClipMajor ? e->ringLen : 1;
+    a.ringTimeStride = e->ringClipMajor ? 1 : e->clipPitch;
+    a.widthRing = e->dRing ? e->dRing + clipOffset * a.ringClipStride : nullptr;
     a.texWave = e->dWave ? e->dWave + clipOffset : nullptr;
     a.clipPitch = e->clipPitch;
     a.nClips = nClips;
@@ -314,9 +326,25 @@ int launchProcess(jb_engine* e, const ProcArgs& a)
         }
     }
     cudaEvent_t start = e->timingEvents[e->timingUsed], stop = e->timingEvents[e->timingUsed + 1];
+    // Path choice: the cooperative (time-parallel) kernel when the chain and the call's shape allow it and
+    // the batch is too small to fill the GPU with one lane per clip; the lane-per-clip kernel otherwise.
+    bool coop = e->coopCapable && e->dCoopScratch != nullptr && jbk_coop_supported(&a) != 0;
+    if (e->pathMode == 1)
+        coop = false;
+    else if (e->pathMode == 2 && !coop)
+        return fail(JB_ERR_UNSUPPORTED, "cooperative path forced but this chain / call shape is not supported by it");
+    else if (e->pathMode == 0 && coop && a.nClips >= kLaneKernelMinClips)
+        coop = false;
     JB_CUDA(cudaEventRecord(start, e->stream));
-    if (jbk_launch_process(&a, e->stream) != 0)
-        return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
+    if (coop) {
+        if (jbk_launch_coop(&a, e->dCoopScratch, e->numSMs, e->stream) != 0)
+            return fail(JB_ERR_CUDA, "%s", jbk_coop_last_error());
+        ++e->coopLaunches;
+    } else {
+        if (jbk_launch_process(&a, e->stream) != 0)
+            return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
+        ++e->laneLaunches;
+    }
     JB_CUDA(cudaEventRecord(stop, e->stream));
     e->timingUsed += 2;
     return JB_OK;
@@ -428,6 +456,18 @@ int jb_prepare(jb_engine* e, double sample_rate, int samples_per_block)
         JB_CUDA(cudaMalloc(&e->dState, sizeof(float) * (size_t) e->totalVars * (size_t) e->clipPitch));
         JB_CUDA(cudaMalloc(&e->dLatest, sizeof(float) * e->chain.size() * JBK_REC * (size_t) e->clipPitch));
     }
+    e->coopCapable = e->chain.size() <= 3;
+    for (size_t i = 0; i < e->chain.size(); ++i) {
+        const int k = e->chain[i];
+        if (!((k == jb::kPunch && i == 0) || k == jb::kWidth || k == jb::kInfer))
+            e->coopCapable = false;
+    }
+    e->ringClipMajor = e->coopCapable;
+    if (e->numSMs == 0) {
+        JB_CUDA(cudaDeviceGetAttribute(&e->numSMs, cudaDevAttrMultiProcessorCount, e->device));
+    }
+    if (e->coopCapable && e->dCoopScratch == nullptr)
+        JB_CUDA(cudaMalloc(&e->dCoopScratch, jbk_coop_scratch_bytes((int) e->chain.size(), e->numSMs)));
     if (hasWidth && (e->dRing == nullptr || ringLen != e->ringLen)) {
         cudaFree(e->dRing);
         e->dRing = nullptr;
@@ -732,6 +772,27 @@ int jb_get_history(jb_engine* e, int slot, int first_block, int n_blocks, jb_met
         JB_CUDA(cudaStreamSynchronize(e->stream));
         unpackRecords(e->hostScratch.data(), e->clipPitch, e->nClips, out + (size_t) b * (size_t) e->nClips);
     }
+    return JB_OK;
+}
+
+int jb_set_path(jb_engine* e, int mode)
+{
+    if (int rc = checkEngine(e))
+        return rc;
+    if (mode < JB_PATH_AUTO || mode > JB_PATH_COOP)
+        return fail(JB_ERR_ARG, "jb_set_path: unknown mode %d", mode);
+    e->pathMode = mode;
+    return JB_OK;
+}
+
+int jb_path_launches(const jb_engine* e, long long* cooperative, long long* lane_per_clip)
+{
+    if (int rc = checkEngine(e))
+        return rc;
+    if (cooperative)
+        *cooperative = e->coopLaunches;
+    if (lane_per_clip)
+        *lane_per_clip = e->laneLaunches;
     return JB_OK;
 }
 

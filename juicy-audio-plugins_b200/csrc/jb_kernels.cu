@@ -15,23 +15,13 @@
 // -fmad=false -ftz=true -prec-div=true -prec-sqrt=true (see Makefile).
 //
 // Reference lines are cited per routine, relative to /root/reference.
-#include "jb_kernels.h"
+#include "jb_device.cuh"
 
-#include <cuda_runtime.h>
 #include <stdio.h>
-
-#define PI_F 3.14159265358979323846f
-#define TWO_PI_F 6.28318530717958647692f
 
 namespace {
 
-enum { K_INFER = 0, K_PUNCH = 1, K_SAT = 2, K_WIDTH = 3, K_COHERE = 4, K_TEXTURE = 5, K_MOTION = 6 };
-
-// juce::jmax / jmin / jlimit / jmap as comparisons
-__device__ __forceinline__ float jmaxf(float a, float b) { return a < b ? b : a; }
-__device__ __forceinline__ float jminf(float a, float b) { return b < a ? b : a; }
-__device__ __forceinline__ float jlimitf(float lo, float hi, float v) { return v < lo ? lo : (hi < v ? hi : v); }
-__device__ __forceinline__ float jmap3(float v, float lo, float hi) { return lo + v * (hi - lo); }
+using namespace jbdev;
 
 // Per-sample transcendentals.  The oracle uses glibc's (nearly correctly rounded)
 // float functions; block-rate pow/log10 are evaluated in fp64 and rounded once,
@@ -118,149 +108,37 @@ struct BlockStats {
         l2 = fma(dl, dl, l2);               // dl*dl is exact in fp64, so the fused form rounds identically
         r2 = fma(dr, dr, r2);
     }
+    __device__ __forceinline__ StatSums sums() const { return StatSums { rms, peak, side, corr, l2, r2 }; }
 };
 
-struct Metrics {
-    float score, emphasis, coherence, synesthesia, fatigueRisk, repetitionDensity, punch, richness, clarity, width, monoSafety;
-};
-
-// The state-dependent walk: two attack/release envelopes, onset state machine,
-// two one-pole band splits (:64-75, :79-84).
+// One analyzer's walk over one block (jb_device.cuh: ana_step / ana_finish) with its state in the SoA arrays.
 struct AnaWalk {
-    float sEnv, lEnv, low, high;
-    int cool;
-    float trAcc = 0.0f, lowAcc = 0.0f, highAcc = 0.0f;
-    int onsets = 0;
-
+    AnaState st;
+    AnaAcc acc;
     __device__ __forceinline__ void load(const Lane& L, int base)
     {
-        sEnv = L.ld(base + AV_SHORT);
-        lEnv = L.ld(base + AV_LONG);
-        low = L.ld(base + AV_LOW);
-        high = L.ld(base + AV_HIGH);
-        cool = L.ldi(base + AV_COOLDOWN);
+        st.sEnv = L.ld(base + AV_SHORT);
+        st.lEnv = L.ld(base + AV_LONG);
+        st.low = L.ld(base + AV_LOW);
+        st.high = L.ld(base + AV_HIGH);
+        st.cool = L.ldi(base + AV_COOLDOWN);
     }
-    __device__ __forceinline__ void step(float mono, const AnaCoef& c)
-    {
-        const float a = fabsf(mono);
-        {   // updateEnvelope (:24-29)
-            const bool up = a > sEnv;
-            sEnv = (up ? c.omaS : c.omrS) * a + (up ? c.aS : c.rS) * sEnv;
-        }
-        {
-            const bool up = a > lEnv;
-            lEnv = (up ? c.omaL : c.omrL) * a + (up ? c.aL : c.rL) * lEnv;
-        }
-        const float tr = jmaxf(0.0f, sEnv - lEnv);
-        trAcc += tr;
-        if (cool > 0)
-            --cool;
-        if (tr > 0.045f && cool <= 0) {
-            ++onsets;
-            cool = c.cooldownLen;
-        }
-        low += c.lowCoeff * (mono - low);
-        high += c.highCoeff * (mono - high);
-        const float hi = mono - high;
-        lowAcc += low * low;
-        highAcc += hi * hi;
-    }
-    // Feature mapping and blend (:94-141); updates the two per-call EMAs and stores the state.
+    __device__ __forceinline__ void step(float mono, const AnaCoef& c) { ana_step(st, acc, mono, c); }
     __device__ Metrics finish(const Lane& L, int base, const BlockStats& s, int n, const AnaCoef& c)
     {
-        const float invN = 1.0f / (float) n;
-        const float rms = sqrtf(s.rms * invN + 1.0e-12f);
-        const float crest = s.peak / (rms + 1.0e-6f);
-        const float lowEnergy = lowAcc * invN;
-        const float highEnergy = highAcc * invN;
-        const float lowHighRatio = lowEnergy / (highEnergy + 1.0e-8f);
-        const float widthRatio = s.side / (s.rms + s.side + 1.0e-8f);
-
-        const float lEnergy = (float) sqrt(s.l2 / (double) n);
-        const float rEnergy = (float) sqrt(s.r2 / (double) n);
-        float corr = s.corr * invN / (lEnergy * rEnergy + 1.0e-6f);
-        corr = jlimitf(-1.0f, 1.0f, corr);
-
-        Metrics m;
-        m.punch = jlimitf(0.0f, 1.0f, 6.0f * trAcc * invN / (rms + 1.0e-5f));
-        m.richness = jlimitf(0.0f, 1.0f, (2.3f - crest) * 0.65f + (rms * 2.0f));
-        float clarity = 1.0f;
-        if (lowHighRatio > 2.5f)
-            clarity -= jlimitf(0.0f, 0.6f, (lowHighRatio - 2.5f) * 0.15f);
-        if (highEnergy > 0.03f)
-            clarity -= jlimitf(0.0f, 0.5f, (highEnergy - 0.03f) * 8.0f);
-        m.clarity = jlimitf(0.0f, 1.0f, clarity);
-        m.width = jlimitf(0.0f, 1.0f, widthRatio * 2.0f);
-        m.monoSafety = jlimitf(0.0f, 1.0f, 0.5f * (corr + 1.0f));
-
-        const float blockSeconds = (float) n / c.srf;
-        const float onsetRate = blockSeconds > 0.0f ? (float) onsets / blockSeconds : 0.0f;
-        float repEma = L.ld(base + AV_REP_EMA);
-        repEma += (onsetRate - repEma) * 0.08f;
-        m.repetitionDensity = jlimitf(0.0f, 1.0f, repEma / 12.0f);
-
-        m.emphasis = jlimitf(0.0f, 1.0f, 0.62f * m.punch + 0.38f * jlimitf(0.0f, 1.0f, trAcc * invN * 8.5f));
-        m.coherence = jlimitf(0.0f, 1.0f, 0.50f * m.clarity + 0.30f * m.monoSafety + 0.20f * (1.0f - fabsf(m.width - 0.45f)));
-        m.synesthesia = jlimitf(0.0f, 1.0f, 0.45f * m.richness + 0.30f * jlimitf(0.0f, 1.0f, lowHighRatio / 3.5f)
-                                                + 0.25f * jlimitf(0.0f, 1.0f, trAcc * invN * 5.0f));
-        const float crestPenalty = jlimitf(0.0f, 1.0f, (1.8f - crest) * 1.1f);
-        const float harshPenalty = jlimitf(0.0f, 1.0f, highEnergy * 12.0f);
-        const float instantFatigue = jlimitf(0.0f, 1.0f, 0.35f * crestPenalty + 0.35f * harshPenalty + 0.30f * m.repetitionDensity);
-        float fatEma = L.ld(base + AV_FAT_EMA);
-        fatEma += (instantFatigue - fatEma) * 0.06f;
-        m.fatigueRisk = jlimitf(0.0f, 1.0f, fatEma);
-
-        float score = 100.0f * (0.30f * m.punch + 0.25f * m.richness + 0.25f * m.clarity + 0.20f * m.width);
-        score *= (0.6f + 0.4f * m.monoSafety);
-        m.score = jlimitf(0.0f, 100.0f, score);
-
-        L.st(base + AV_SHORT, sEnv);
-        L.st(base + AV_LONG, lEnv);
-        L.st(base + AV_LOW, low);
-        L.st(base + AV_HIGH, high);
-        L.sti(base + AV_COOLDOWN, cool);
-        L.st(base + AV_REP_EMA, repEma);
-        L.st(base + AV_FAT_EMA, fatEma);
+        st.repEma = L.ld(base + AV_REP_EMA);
+        st.fatEma = L.ld(base + AV_FAT_EMA);
+        const Metrics m = ana_finish(st, acc, s.sums(), n, c);
+        L.st(base + AV_SHORT, st.sEnv);
+        L.st(base + AV_LONG, st.lEnv);
+        L.st(base + AV_LOW, st.low);
+        L.st(base + AV_HIGH, st.high);
+        L.sti(base + AV_COOLDOWN, st.cool);
+        L.st(base + AV_REP_EMA, st.repEma);
+        L.st(base + AV_FAT_EMA, st.fatEma);
         return m;
     }
 };
-
-// Output parameter as the host reads it back: setValueNotifyingHost(convertTo0to1(v))
-// then the APVTS adapter's denormalise(getValue()) (e.g. JuicyPunch/PluginProcessor.cpp:56-62).
-__device__ __forceinline__ float output_param(float v, float lo, float hi)
-{
-    const float n = jlimitf(0.0f, 1.0f, (v - lo) / (hi - lo));
-    const float stored = jlimitf(lo, hi, lo + (hi - lo) * n);
-    const float n2 = jlimitf(0.0f, 1.0f, (stored - lo) / (hi - lo));
-    return jlimitf(lo, hi, lo + (hi - lo) * n2);
-}
-
-__device__ void write_record(const ProcArgs& a, int slot, long long clip, int blockAbs, const float* rec)
-{
-    float* dst = a.latest + (long long) slot * JBK_REC * a.clipPitch + clip;
-#pragma unroll
-    for (int f = 0; f < JBK_REC; ++f)
-        dst[(long long) f * a.clipPitch] = rec[f];
-    if (a.hist != nullptr && blockAbs < a.histMaxBlocks) {
-        float* h = a.hist + ((long long) blockAbs * a.chainLen + slot) * JBK_REC * a.clipPitch + clip;
-#pragma unroll
-        for (int f = 0; f < JBK_REC; ++f)
-            h[(long long) f * a.clipPitch] = rec[f];
-    }
-}
-
-// getLatestMetrics() of the ordinary plugins: 8 mailboxes (e.g. JuicyPunch/PluginProcessor.cpp:115-123,190-202)
-__device__ void publish_plain(const ProcArgs& a, int slot, long long clip, int blockAbs, const Metrics& m, float preScore, float aux)
-{
-    float rec[JBK_REC];
-    rec[0] = m.score; rec[1] = preScore; rec[2] = m.score;
-    rec[3] = 0.0f; rec[4] = 0.0f; rec[5] = 0.0f; rec[6] = 0.0f; rec[7] = 0.0f;
-    rec[8] = m.punch; rec[9] = m.richness; rec[10] = m.clarity; rec[11] = m.width; rec[12] = m.monoSafety;
-    rec[13] = output_param(m.score, 0.0f, 100.0f);
-    rec[14] = aux;
-    rec[15] = 0.0f;
-    write_record(a, slot, clip, blockAbs, rec);
-}
 
 // ------------------------------------------------------------------ plugin DSP ("main" part of a sweep)
 // Interface: writes() (must the sweep store samples), kSeqChannels (channel 0's whole block
@@ -395,8 +273,8 @@ struct MainWidth : MainBase {
         c = d.c.width;
         width = c.width; // re-read from the parameter every block (:93)
         wpos = L.ldi(d.stateBase + AV_COUNT + WV_WPOS);
-        ring = L.a.widthRing + L.clip;
-        pitch = L.a.clipPitch;
+        ring = L.a.widthRing + L.clip * L.a.ringClipStride;
+        pitch = L.a.ringTimeStride;
     }
     __device__ __forceinline__ void step(float& l, float& r)
     {
@@ -973,19 +851,8 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
         mainPart.store(L, d);
         Metrics m = post.finish(L, d.stateBase, stats, n, ana);
         const float preScore = L.ld(d.stateBase + AV_PRE_SCORE);
-        if (d.kind == K_INFER) { // JuicyInfer/PluginProcessor.cpp:81-101,164-181
-            m.score = jlimitf(0.0f, 100.0f, m.score * d.c.infer.sensitivity);
-            float rec[JBK_REC];
-            rec[0] = m.score; rec[1] = preScore; rec[2] = m.score;
-            rec[3] = m.emphasis; rec[4] = m.coherence; rec[5] = m.synesthesia; rec[6] = m.fatigueRisk; rec[7] = m.repetitionDensity;
-            rec[8] = m.emphasis; rec[9] = m.coherence; rec[10] = m.synesthesia; rec[11] = m.fatigueRisk; rec[12] = m.repetitionDensity;
-            rec[13] = output_param(m.score, 0.0f, 100.0f);
-            rec[14] = 0.0f; rec[15] = 0.0f;
-            write_record(a, mainSlot, clip, blockAbs, rec);
-        } else {
-            const float aux = d.kind == K_COHERE ? L.ld(d.stateBase + AV_COUNT + CV_FIT) : 0.0f;
-            publish_plain(a, mainSlot, clip, blockAbs, m, preScore, aux);
-        }
+        const float aux = d.kind == K_COHERE ? L.ld(d.stateBase + AV_COUNT + CV_FIT) : 0.0f;
+        publish_record(a, mainSlot, clip, blockAbs, m, preScore, aux);
     }
     if constexpr (Pre::kHas) {
         const SlotDesc& d = a.slot[preSlot];
@@ -1135,6 +1002,7 @@ extern "C" {
 
 const char* jbk_last_cuda_error(void) { return g_cudaErr; }
 long long jbk_launch_count(void) { return g_launches; }
+void jbk_note_launch(void) { ++g_launches; }
 
 int jbk_launch_process(const ProcArgs* args, void* stream)
 {

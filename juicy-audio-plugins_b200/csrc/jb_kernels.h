@@ -9,6 +9,7 @@
 // per-sample arithmetic (compiled with -fmad=false -ftz=true -prec-div=true
 // -prec-sqrt=true) and the per-sample / per-block transcendentals.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #define JBK_MAX_CHAIN 8
@@ -141,7 +142,8 @@ struct ProcArgs {
     float* state;          // SoA state, clipPitch floats per variable
     float* latest;         // [slot][JBK_REC][clipPitch]
     float* hist;           // optional [block][slot][JBK_REC][clipPitch], or null
-    float* widthRing;      // [ringLen][clipPitch]      (wetR history of the Width slot)
+    float* widthRing;      // wetR history of the Width slot: element (clip, t) at clip*ringClipStride + t*ringTimeStride
+    long long ringClipStride, ringTimeStride; // time-major [ringLen][clipPitch] (1, clipPitch) or clip-major [clip][ringLen] (ringLen, 1)
     float* texWave;        // [2][waveSize][clipPitch]  (Texture waveguides)
     long long clipPitch;
     int nClips, nCh, nSamples, blockSize;
@@ -162,6 +164,12 @@ int jbk_launch_synth(float* dAudio, int kind, long long firstClip, int nClips, i
                      double sampleRate, unsigned int seed, void* stream);
 const char* jbk_last_cuda_error(void);
 long long jbk_launch_count(void);
+void jbk_note_launch(void);
+// jb_coop.cu
+int jbk_coop_supported(const ProcArgs* args);
+size_t jbk_coop_scratch_bytes(int chainLen, int numSMs);
+int jbk_launch_coop(const ProcArgs* args, float* monoScratch, int numSMs, void* stream);
+const char* jbk_coop_last_error(void);
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,8 @@ def lib():
         "jb_copy_to_device": (ci, [ci, vp, vp, ctypes.c_size_t]),
         "jb_copy_to_host": (ci, [ci, vp, vp, ctypes.c_size_t]),
         "jb_kernel_time_ms": (ci, [vp, ctypes.POINTER(cd), ctypes.POINTER(cll)]),
+        "jb_set_path": (ci, [vp, ci]),
+        "jb_path_launches": (ci, [vp, ctypes.POINTER(cll), ctypes.POINTER(cll)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -320,6 +322,16 @@ class BatchProcessor:
         if n_blocks > 0:
             _check(lib().jb_get_history(self._h, self.slot(slot), int(first_block), int(n_blocks), out.ctypes.data))
         return out
+
+    def set_path(self, mode):
+        """Render-kernel choice: "auto", "lane" (one lane per clip) or "coop" (block-cooperative)."""
+        _check(lib().jb_set_path(self._h, {"auto": 0, "lane": 1, "coop": 2}[mode]))
+
+    def path_launches(self):
+        """(cooperative, lane_per_clip) render-kernel launches so far."""
+        c, l = ctypes.c_longlong(), ctypes.c_longlong()
+        _check(lib().jb_path_launches(self._h, ctypes.byref(c), ctypes.byref(l)))
+        return c.value, l.value
 
     def kernel_time_ms(self):
         """(milliseconds, launches) spent in the render kernel since the last call (CUDA events

@@ -192,3 +192,79 @@ def test_silence_scores_forty_and_lanes_are_independent(jb):
     assert np.array_equal(eng.getLatestMetrics(6)[5], solo.getLatestMetrics(6)[0])
     eng.close()
     solo.close()
+
+
+# ---------------------------------------------------------------- the block-cooperative kernel (jb_coop.cu)
+
+COOP_CHAINS = [["JuicyPunch", "JuicyWidth"], ["JuicyPunch"], ["JuicyWidth"], ["JuicyInfer"],
+               ["JuicyPunch", "JuicyWidth", "JuicyInfer"], ["JuicyWidth", "JuicyInfer"]]
+
+
+@pytest.mark.parametrize("chain", COOP_CHAINS, ids=["+".join(c) for c in COOP_CHAINS])
+def test_coop_kernel_matches_oracle_and_lane_kernel(chain, jb, port):
+    """Forced cooperative path vs the oracle (tolerances of BASELINE.json) and vs the lane-per-clip kernel."""
+    n_clips, n = 70, 2 * BLOCK + 300
+    clips = jb.synth_clips("mixed", 7, n_clips, n)
+    clips[:, :, :] *= np.linspace(0.3, 1.6, n_clips, dtype=np.float32)[:, None, None]
+    outs, recs = {}, {}
+    for path in ("coop", "lane"):
+        eng = jb.BatchProcessor(chain, n_clips)
+        eng.set_path(path)
+        eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+        eng.enableHistory(4)
+        outs[path] = eng.processBlock(clips)
+        recs[path] = [eng.getHistory(slot) for slot in range(len(chain))]
+        coop_launches, lane_launches = eng.path_launches()
+        assert (coop_launches > 0 and lane_launches == 0) if path == "coop" else (lane_launches > 0 and coop_launches == 0)
+        eng.close()
+    ref, hists = oracle_render(port, chain, clips)
+    assert_samples_close(outs["coop"], ref, "coop " + "+".join(chain))
+    assert_samples_close(outs["coop"], outs["lane"], "coop vs lane " + "+".join(chain))
+    for slot in range(len(chain)):
+        want = np.stack([h[slot] for h in hists], axis=1)  # [block][clip][16]
+        assert_records_close(recs["coop"][slot], want, "coop %s slot %d" % ("+".join(chain), slot))
+        assert_records_close(recs["coop"][slot], recs["lane"][slot], "coop vs lane slot %d" % slot)
+
+
+@pytest.mark.parametrize("block", [64, 256, 500, 512])
+def test_coop_kernel_block_sizes_and_split_calls(block, jb, port):
+    chain = ["JuicyPunch", "JuicyWidth"]
+    n_clips, n = 5, 2600
+    clips = jb.synth_clips("drum", 9, n_clips, n)
+    eng = jb.BatchProcessor(chain, n_clips)
+    eng.set_path("coop")
+    eng.setParameter("haasMs", 3.0, 1)  # 144-sample delay: the ring read lands inside the same step
+    eng.prepareToPlay(SAMPLE_RATE, block)
+    out = eng.processBlock(clips)
+    ref, hists = oracle_render(port, chain, clips, block=block, params={1: {"haasMs": 3.0}})
+    assert_samples_close(out, ref, "coop block %d" % block)
+    for slot in range(len(chain)):
+        assert_records_close(eng.getLatestMetrics(slot), np.stack([h[slot][-1] for h in hists]), "coop block %d" % block)
+    # two host callbacks == one (state carried through the SoA arrays between launches)
+    eng.reset()
+    cut = 3 * block
+    first = eng.processBlock(clips[:, :, :cut])
+    second = eng.processBlock(clips[:, :, cut:])
+    assert np.array_equal(np.concatenate([first, second], axis=2), out)
+    eng.close()
+
+
+def test_coop_kernel_many_groups(jb, port):
+    """More clips than one wave of CTA groups (148 x 32): persistent CTAs loop over groups."""
+    chain = ["JuicyPunch", "JuicyWidth"]
+    n_clips, n = 148 * 32 + 37, BLOCK + 256
+    clips = jb.synth_clips("mixed", 3, n_clips, n)
+    outs = {}
+    for path in ("coop", "lane"):
+        eng = jb.BatchProcessor(chain, n_clips)
+        eng.set_path(path)
+        eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+        outs[path] = (eng.processBlock(clips), eng.getLatestMetrics(0), eng.getLatestMetrics(1))
+        eng.close()
+    assert_samples_close(outs["coop"][0], outs["lane"][0], "coop vs lane, many groups")
+    assert_records_close(outs["coop"][1], outs["lane"][1], "many groups slot 0")
+    assert_records_close(outs["coop"][2], outs["lane"][2], "many groups slot 1")
+    pick = list(range(0, n_clips, 151))
+    ref, hists = oracle_render(port, chain, clips[pick])
+    assert_samples_close(outs["coop"][0][pick], ref, "coop vs oracle, many groups")
+    assert_records_close(outs["coop"][2][pick], np.stack([h[1][-1] for h in hists]), "many groups records")
