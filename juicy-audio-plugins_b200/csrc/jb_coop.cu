@@ -41,17 +41,21 @@ constexpr int CO_PITCH = CO_T + 4;   // floats per tile row (+16 B: row-walking 
 constexpr int CO_BLOCKMAX = 512;     // largest host block size this path takes
 constexpr int CO_MAXCHAIN = 3;       // plugins per chain on this path
 constexpr int CO_NSIG = CO_MAXCHAIN + 1;
+// Warp roles: [0] producer, [1, 2] scouts, then nAna "envelope" analyzer warps, nAna "band" analyzer
+// warps (nAna = ceil(chainLen * groupClips / 32), decided per launch), and every remaining warp is bulk.
 constexpr int CO_W_PRODUCER = 0;
-constexpr int CO_W_SCOUT = 1, CO_NSCOUT = CO_ROWS / 32;                      // 2 warps
-constexpr int CO_W_ANA = CO_W_SCOUT + CO_NSCOUT, CO_NANA = CO_GMAX * CO_MAXCHAIN / 32; // 3 warps
-constexpr int CO_W_BULK = CO_W_ANA + CO_NANA, CO_NBULK = 14;
-constexpr int CO_WARPS = CO_W_BULK + CO_NBULK;                               // 20
-constexpr int CO_THREADS = CO_WARPS * 32;                                    // 640
+constexpr int CO_W_SCOUT = 1, CO_NSCOUT = CO_ROWS / 32; // 2 warps
+constexpr int CO_W_ANA = CO_W_SCOUT + CO_NSCOUT;
+constexpr int CO_ANA_LANES = CO_GMAX * CO_MAXCHAIN;     // 96
+constexpr int CO_WARPS = 21;
+constexpr int CO_THREADS = CO_WARPS * 32;               // 672
+constexpr int CO_BAR_ANA = 1;                           // named barrier of the analyzer warps
 
 struct CoopSmem {
     float tile[2][CO_ROWS][CO_PITCH];           // 133,120 B
     float2 ckpt[2][CO_ROWS][CO_T / CO_CH];      //  32,768 B  Punch (fast, slow) at every chunk start
-    float stats[2][CO_GMAX][CO_NSIG][8];        //   8,192 B  rms, peak, side, corr, l2, r2 per (block parity, clip, signal)
+    float stats[2][CO_GMAX][CO_NSIG][8];        //   8,192 B  sum m^2, peak, sum l^2, sum r^2, sum l*r per (block parity, clip, signal)
+    float bandAcc[2][CO_ANA_LANES][2];          //   low/high band energies handed from the band lanes to the envelope lanes
     float widthTab[CO_BLOCKMAX + 1];            //   width * dyn^k, k multiplies applied in sample order
     int widthPos[CO_GMAX];                      //   ring write position of the step's first sample
     int widthCount[CO_GMAX];                    //   multiplies so far in the current host block
@@ -202,32 +206,65 @@ __device__ __forceinline__ void width_chunk(float (&l)[CO_CH], float (&r)[CO_CH]
     warpTotal = __shfl_sync(0xffffffffu, incl, 31);
     const int base = kStart + incl - cnt;
 
-    float wetL[CO_CH];
-    int wp = wpos0 + lane * CO_CH;
-    wp -= wp >= c.ringLen ? c.ringLen : 0; // wpos0 < ringLen and lane*CO_CH < CO_T <= ringLen
+    float wetL[CO_CH], wetR[CO_CH];
 #pragma unroll
     for (int i = 0; i < CO_CH; ++i) {
         const float width = tab[base + kk[i]];
         const float mid = 0.5f * (l[i] + r[i]);
         const float side = 0.5f * (l[i] - r[i]) * (1.0f + width);
         wetL[i] = mid + side;
-        const float wetR = mid - side;
-        int p = wp + i;
-        p -= p >= c.ringLen ? c.ringLen : 0;
-        if (i < nValid)
-            ring[p] = wetR;
+        wetR[i] = mid - side;
+    }
+    int wp = wpos0 + lane * CO_CH;
+    wp -= wp >= c.ringLen ? c.ringLen : 0; // wpos0 < ringLen and lane*CO_CH < CO_T <= ringLen
+    // 16-byte ring accesses when write position, delay and ring length are all multiples of 4 samples
+    // (the usual case: 2880-sample ring, 576-sample delay, steps of 256); single floats otherwise.
+    const bool vec = ((wpos0 | c.ringLen | c.delaySamples) & 3) == 0;
+    if (vec) {
+#pragma unroll
+        for (int g = 0; g < CO_CH / 4; ++g) {
+            int p = wp + 4 * g;
+            p -= p >= c.ringLen ? c.ringLen : 0;
+            if (4 * g < nValid)
+                *reinterpret_cast<float4*>(ring + p) = make_float4(wetR[4 * g], wetR[4 * g + 1], wetR[4 * g + 2], wetR[4 * g + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CO_CH; ++i) {
+            int p = wp + i;
+            p -= p >= c.ringLen ? c.ringLen : 0;
+            if (i < nValid)
+                ring[p] = wetR[i];
+        }
     }
     __syncwarp(); // the delayed read below may land on a value another lane wrote in this step
+    if (vec) {
+#pragma unroll
+        for (int g = 0; g < CO_CH / 4; ++g) {
+            int p = wp + 4 * g;
+            p -= p >= c.ringLen ? c.ringLen : 0;
+            int rp = p - c.delaySamples;
+            rp += rp < 0 ? c.ringLen : 0;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (4 * g < nValid)
+                v = __ldcg(reinterpret_cast<const float4*>(ring + rp));
+            wetR[4 * g] = v.x; wetR[4 * g + 1] = v.y; wetR[4 * g + 2] = v.z; wetR[4 * g + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CO_CH; ++i) {
+            int p = wp + i;
+            p -= p >= c.ringLen ? c.ringLen : 0;
+            int rp = p - c.delaySamples;
+            rp += rp < 0 ? c.ringLen : 0;
+            wetR[i] = (i < nValid) ? __ldcg(ring + rp) : 0.0f;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < CO_CH; ++i) {
-        int p = wp + i;
-        p -= p >= c.ringLen ? c.ringLen : 0;
-        int rp = p - c.delaySamples;
-        rp += rp < 0 ? c.ringLen : 0;
-        const float wetR = (i < nValid) ? __ldcg(ring + rp) : 0.0f;
         const float dryL = l[i], dryR = r[i];
         l[i] = (dryL + c.mix * (wetL[i] - dryL)) * c.outGain;
-        r[i] = (dryR + c.mix * (wetR - dryR)) * c.outGain;
+        r[i] = (dryR + c.mix * (wetR[i] - dryR)) * c.outGain;
     }
 }
 
@@ -261,88 +298,125 @@ __device__ __forceinline__ void mask_chunk(float (&l)[CO_CH], float (&r)[CO_CH],
     }
 }
 
-__device__ __forceinline__ float warp_sum(float v)
+// Sum of four values over the warp in 6 shuffles: each butterfly stage halves the values a lane carries.
+// The totals land on lane 0 (every lane with lane % 4 == 0 ends up holding one of the four).
+__device__ __forceinline__ void warp_sum4(float& v0, float& v1, float& v2, float& v3, int lane)
 {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1)
-        v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v)
-{
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1)
-        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
-    return v;
+    {   // stage 1 (xor 16): lower half keeps (v0, v1), upper half keeps (v2, v3)
+        const bool hi = (lane & 16) != 0;
+        const float s0 = hi ? v0 : v2, s1 = hi ? v1 : v3;
+        const float k0 = hi ? v2 : v0, k1 = hi ? v3 : v1;
+        v0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+        v1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+    }
+    {   // stage 2 (xor 8): keep one of the two
+        const bool hi = (lane & 8) != 0;
+        const float send = hi ? v0 : v1, keep = hi ? v1 : v0;
+        v0 = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    v0 += __shfl_xor_sync(0xffffffffu, v0, 4);
+    v0 += __shfl_xor_sync(0xffffffffu, v0, 2);
+    v0 += __shfl_xor_sync(0xffffffffu, v0, 1);
+    // lane bits (16, 8) now select which total v0 is: 00 -> v0, 01 -> v1, 10 -> v2, 11 -> v3
+    v1 = __shfl_sync(0xffffffffu, v0, 8);
+    v2 = __shfl_sync(0xffffffffu, v0, 16);
+    v3 = __shfl_sync(0xffffffffu, v0, 24);
 }
 
 // The order-independent sums of analyze() over this lane's chunk of one signal
 // (JuicinessAnalyzer.cpp:76-77,86-91,105-106), tree-reduced over the warp and added to the
-// block's running totals; the mono sum of every sample goes to the analyzer lanes' scratch ring.
+// block's running totals.  Kept: sum mono^2, max |mono|, sum l^2, sum r^2, sum l*r; the side
+// energy follows from mid^2 + side^2 = (l^2 + r^2) / 2 (load_stats).  The mono sum of every sample
+// goes to the analyzer lanes' scratch ring.
 __device__ __forceinline__ void signal_stats(const float (&l)[CO_CH], const float (&r)[CO_CH], float* acc, bool firstStep,
                                              float* monoDst, int lane, int nValid)
 {
     float mono[CO_CH];
-    float rms = 0.0f, peak = 0.0f, side = 0.0f, corr = 0.0f, l2 = 0.0f, r2 = 0.0f;
+    float rms = 0.0f, peak = 0.0f, corr = 0.0f, l2 = 0.0f, r2 = 0.0f;
 #pragma unroll
     for (int i = 0; i < CO_CH; ++i) {
         const float m = 0.5f * (l[i] + r[i]);
         mono[i] = m;
         rms = fmaf(m, m, rms);
         peak = fmaxf(peak, fabsf(m));
-        const float s = 0.5f * (l[i] - r[i]);
-        side = fmaf(s, s, side);
         corr = fmaf(l[i], r[i], corr);
         l2 = fmaf(l[i], l[i], l2);
         r2 = fmaf(r[i], r[i], r2);
     }
     if (nValid > 0)
-        __stcg(reinterpret_cast<float4*>(monoDst), make_float4(mono[0], mono[1], mono[2], mono[3]));
+        *reinterpret_cast<float4*>(monoDst) = make_float4(mono[0], mono[1], mono[2], mono[3]);
     if (nValid > 4)
-        __stcg(reinterpret_cast<float4*>(monoDst) + 1, make_float4(mono[4], mono[5], mono[6], mono[7]));
-    rms = warp_sum(rms);
-    peak = warp_max(peak);
-    side = warp_sum(side);
-    corr = warp_sum(corr);
-    l2 = warp_sum(l2);
-    r2 = warp_sum(r2);
+        *(reinterpret_cast<float4*>(monoDst) + 1) = make_float4(mono[4], mono[5], mono[6], mono[7]);
+    warp_sum4(rms, l2, r2, corr, lane);
+    peak = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(peak))); // non-negative floats order like their bits
     if (lane == 0) {
         if (firstStep) {
-            acc[0] = rms; acc[1] = peak; acc[2] = side; acc[3] = corr; acc[4] = l2; acc[5] = r2;
+            acc[0] = rms; acc[1] = peak; acc[2] = l2; acc[3] = r2; acc[4] = corr;
         } else {
-            acc[0] += rms; acc[1] = fmaxf(acc[1], peak); acc[2] += side; acc[3] += corr; acc[4] += l2; acc[5] += r2;
+            acc[0] += rms; acc[1] = fmaxf(acc[1], peak); acc[2] += l2; acc[3] += r2; acc[4] += corr;
         }
     }
 }
 
 // ---------------------------------------------------------------- analyzer lanes
+// One lane walks one analyzer's samples in order.  BANDS = false: envelopes + onset machine;
+// BANDS = true: the two band-split one-poles.  Mono samples come from the L2-resident scratch ring,
+// 16 samples (4 x 16 B) prefetched ahead.
+template <bool BANDS>
+__device__ __forceinline__ void ana_steps4(AnaState& st, AnaAcc& acc, const float4 v, const AnaCoef& c)
+{
+    if (BANDS) {
+        ana_step_bands(st, acc, v.x, c);
+        ana_step_bands(st, acc, v.y, c);
+        ana_step_bands(st, acc, v.z, c);
+        ana_step_bands(st, acc, v.w, c);
+    } else {
+        ana_step_env(st, acc, v.x, c);
+        ana_step_env(st, acc, v.y, c);
+        ana_step_env(st, acc, v.z, c);
+        ana_step_env(st, acc, v.w, c);
+    }
+}
+template <bool BANDS>
 __device__ __forceinline__ void ana_walk(AnaState& st, AnaAcc& acc, const float* stream, int n, const AnaCoef& c)
 {
     const float4* p = reinterpret_cast<const float4*>(stream);
-    const int n4 = n >> 2; // the path requires n % 4 == 0
-    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
-    if (0 < n4) q0 = __ldcg(p + 0);
-    if (1 < n4) q1 = __ldcg(p + 1);
-    if (2 < n4) q2 = __ldcg(p + 2);
-    if (3 < n4) q3 = __ldcg(p + 3);
-    for (int q = 0; q < n4; ++q) {
-        const float4 cur = q0;
-        q0 = q1; q1 = q2; q2 = q3;
-        if (q + 4 < n4)
-            q3 = __ldcg(p + q + 4);
-        ana_step(st, acc, cur.x, c);
-        ana_step(st, acc, cur.y, c);
-        ana_step(st, acc, cur.z, c);
-        ana_step(st, acc, cur.w, c);
+    const int n4 = n >> 2;      // the path requires n % 4 == 0
+    const int nGroups = n4 >> 2; // groups of 16 samples, fetched two groups (32 samples) ahead of their use
+    float4 c0, c1, c2, c3, d0, d1, d2, d3;
+    c0 = c1 = c2 = c3 = d0 = d1 = d2 = d3 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (nGroups > 0) { c0 = p[0]; c1 = p[1]; c2 = p[2]; c3 = p[3]; }
+    if (nGroups > 1) { d0 = p[4]; d1 = p[5]; d2 = p[6]; d3 = p[7]; }
+    for (int g = 0; g < nGroups; ++g) {
+        float4 e0 = c0, e1 = c0, e2 = c0, e3 = c0;
+        if (g + 2 < nGroups) {
+            const float4* q = p + 4 * (g + 2);
+            e0 = q[0]; e1 = q[1]; e2 = q[2]; e3 = q[3];
+        }
+        ana_steps4<BANDS>(st, acc, c0, c);
+        ana_steps4<BANDS>(st, acc, c1, c);
+        ana_steps4<BANDS>(st, acc, c2, c);
+        ana_steps4<BANDS>(st, acc, c3, c);
+        c0 = d0; c1 = d1; c2 = d2; c3 = d3;
+        d0 = e0; d1 = e1; d2 = e2; d3 = e3;
     }
+    for (int q = 4 * nGroups; q < n4; ++q)
+        ana_steps4<BANDS>(st, acc, p[q], c);
 }
 
 __device__ __forceinline__ StatSums load_stats(const float* s)
 {
     StatSums t;
-    t.rms = s[0]; t.peak = s[1]; t.side = s[2]; t.corr = s[3];
-    t.l2 = (double) s[4]; t.r2 = (double) s[5];
+    t.rms = s[0]; t.peak = s[1];
+    t.l2 = (double) s[2]; t.r2 = (double) s[3];
+    t.corr = s[4];
+    t.side = jmaxf(0.0f, 0.5f * (s[2] + s[3]) - s[0]); // sum side^2 = sum (l^2 + r^2) / 2 - sum mid^2
     return t;
+}
+
+__device__ __forceinline__ void named_barrier(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 struct CoopArgs {
@@ -361,6 +435,16 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
     const int L = a.chainLen;
     const int nSig = L + 1;
     const AnaCoef ana = a.ana;
+
+    // roles (uniform over the launch)
+    const int nAna = (L * ca.groupClips + 31) / 32;          // envelope-analyzer warps; as many band-analyzer warps
+    const int wBand = CO_W_ANA + nAna, wBulk = CO_W_ANA + 2 * nAna;
+    const int nBulk = CO_WARPS - wBulk;
+    const bool isProducerWarp = warp == CO_W_PRODUCER;
+    const bool isScoutWarp = warp >= CO_W_SCOUT && warp < CO_W_ANA;
+    const bool isEnvWarp = warp >= CO_W_ANA && warp < wBand;
+    const bool isBandWarp = warp >= wBand && warp < wBulk;
+    const int anaThreads = 2 * nAna * 32;
 
     if (threadIdx.x == 0) {
         mbar_init(&sm.bar[0], 1);
@@ -396,17 +480,17 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
         // scout: Punch envelopes of row (clip, ch)
         float scF = 0.0f, scS = 0.0f;
         const int scRow = (warp - CO_W_SCOUT) * 32 + lane;
-        const bool isScout = warp >= CO_W_SCOUT && warp < CO_W_SCOUT + CO_NSCOUT && punchFirst && scRow < rows;
+        const bool isScout = isScoutWarp && punchFirst && scRow < rows;
         if (isScout) {
             const long long clip = clip0 + (scRow >> 1);
             const int b = a.slot[0].stateBase + AV_COUNT;
             scF = a.state[(long long) (b + PV_FAST0 + (scRow & 1)) * a.clipPitch + clip];
             scS = a.state[(long long) (b + PV_SLOW0 + (scRow & 1)) * a.clipPitch + clip];
         }
-        // analyzer: lane <-> (plugin slot, clip)
-        const int anaIdx = (warp - CO_W_ANA) * 32 + lane;
-        const int anaSlot = anaIdx / CO_GMAX, anaClip = anaIdx % CO_GMAX;
-        const bool isAna = warp >= CO_W_ANA && warp < CO_W_ANA + CO_NANA && anaSlot < L && anaClip < G;
+        // analyzers: lane <-> (plugin slot, clip), once in an envelope warp and once in a band warp
+        const int anaIdx = (warp - (isBandWarp ? wBand : CO_W_ANA)) * 32 + lane;
+        const int anaSlot = anaIdx / ca.groupClips, anaClip = anaIdx % ca.groupClips;
+        const bool isAna = (isEnvWarp || isBandWarp) && anaSlot < L && anaClip < G;
         AnaState ast {};
         float preScore = 0.0f;
         if (isAna) {
@@ -424,7 +508,6 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             sm.widthCount[threadIdx.x] = 0;
         }
 
-        // ---- prologue: load step 0 and scout it
         Cursor cur = cursor_at(a, 0, 0);
         auto issue_load = [&](const Cursor& c, unsigned step) {
             // producer warp: one bulk copy per (clip, channel) row
@@ -459,12 +542,51 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                 }
             }
         };
+        // One analyze() call of host block `blk` on signal `sig` (its mono samples and plain sums were left by
+        // the bulk warps): both analyzer roles walk, the band lanes hand their energies over, the envelope
+        // lanes finish.  Called by all lanes of the analyzer warps (named barrier inside).
+        int anaCalls = 0;
+        auto analyze = [&](int blk, int n, int sig) -> Metrics {
+            const int par = blk & 1, hand = anaCalls & 1;
+            ++anaCalls;
+            AnaAcc acc;
+            const float* stream = monoCta + ((size_t) anaClip * nSig + sig) * 2 * CO_BLOCKMAX + par * CO_BLOCKMAX;
+            if (isAna) {
+                if (isBandWarp) {
+                    ana_walk<true>(ast, acc, stream, n, ana);
+                    sm.bandAcc[hand][anaIdx][0] = acc.lowAcc;
+                    sm.bandAcc[hand][anaIdx][1] = acc.highAcc;
+                } else {
+                    ana_walk<false>(ast, acc, stream, n, ana);
+                }
+            }
+            named_barrier(CO_BAR_ANA, anaThreads);
+            Metrics m {};
+            if (isAna && isEnvWarp) {
+                acc.lowAcc = sm.bandAcc[hand][anaIdx][0];
+                acc.highAcc = sm.bandAcc[hand][anaIdx][1];
+                m = ana_finish(ast, acc, load_stats(sm.stats[par][anaClip][sig]), n, ana);
+            }
+            return m;
+        };
+        auto analyze_pre = [&](int blk, int n) { // analyze(buffer) before the plugin's DSP (e.g. JuicyPunch/PluginProcessor.cpp:82)
+            const Metrics m = analyze(blk, n, anaSlot);
+            if (isAna && isEnvWarp)
+                preScore = m.score;
+        };
+        auto analyze_post = [&](int blk, int n) { // ... and after it (:114), then the mailboxes (:115-123)
+            const Metrics m = analyze(blk, n, anaSlot + 1);
+            if (isAna && isEnvWarp)
+                publish_record(a, anaSlot, clip0 + anaClip, a.histFirstBlock + blk, m, preScore, 0.0f);
+        };
+
+        // ---- prologue: load step 0 and scout it
         __syncthreads(); // widthPos/widthCount visible; previous group's tiles are drained
-        if (warp == CO_W_PRODUCER) {
+        if (isProducerWarp) {
             bulk_wait_read();
             issue_load(cur, gstep);
         }
-        if (warp >= CO_W_SCOUT && warp < CO_W_SCOUT + CO_NSCOUT)
+        if (isScoutWarp)
             scout_step(cur, gstep);
         __syncthreads();
 
@@ -474,39 +596,31 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             const unsigned step = gstep, slot = gstep & 1;
             const int blockPar = cur.blk & 1;
 
-            if (warp == CO_W_PRODUCER) {
+            if (isProducerWarp) {
                 if (nxt.valid) {
                     bulk_wait_read(); // the store that last read the other slot has drained
                     issue_load(nxt, step + 1);
                 }
-            } else if (warp < CO_W_SCOUT + CO_NSCOUT) {
+            } else if (isScoutWarp) {
                 if (nxt.valid)
                     scout_step(nxt, step + 1);
-            } else if (warp < CO_W_ANA + CO_NANA) {
+            } else if (isEnvWarp || isBandWarp) {
                 // analyzers run one host block behind: pre-analysis of block blk-1 during the first
                 // step of block blk, post-analysis during the second (or both, if blk is one step long)
-                if (isAna && cur.blk > 0) {
-                    const int pb = cur.blk - 1, ppar = pb & 1, pn = a.blockSize;
+                if (cur.blk > 0) {
                     const bool single = cur.nBlk <= CO_T;
-                    const float* streams = monoCta + ((size_t) anaClip * nSig) * 2 * CO_BLOCKMAX + ppar * CO_BLOCKMAX;
-                    if (cur.off == 0) { // analyze(buffer) before the plugin's DSP (e.g. JuicyPunch/PluginProcessor.cpp:82)
-                        AnaAcc acc;
-                        ana_walk(ast, acc, streams + (size_t) anaSlot * 2 * CO_BLOCKMAX, pn, ana);
-                        preScore = ana_finish(ast, acc, load_stats(sm.stats[ppar][anaClip][anaSlot]), pn, ana).score;
-                    }
-                    if (single || cur.off == CO_T) { // analyze(buffer) after it (:114)
-                        AnaAcc acc;
-                        ana_walk(ast, acc, streams + (size_t) (anaSlot + 1) * 2 * CO_BLOCKMAX, pn, ana);
-                        const Metrics m = ana_finish(ast, acc, load_stats(sm.stats[ppar][anaClip][anaSlot + 1]), pn, ana);
-                        publish_record(a, anaSlot, clip0 + anaClip, a.histFirstBlock + pb, m, preScore, 0.0f);
-                    }
+                    if (cur.off == 0)
+                        analyze_pre(cur.blk - 1, a.blockSize);
+                    if (single || cur.off == CO_T)
+                        analyze_post(cur.blk - 1, a.blockSize);
                 }
             } else {
                 // ---- bulk warps
                 mbar_wait(&sm.bar[slot], (step >> 1) & 1);
                 const int nValid = max(0, min(CO_CH, cur.n - lane * CO_CH));
                 const bool firstStep = cur.off == 0;
-                for (int ci = warp - CO_W_BULK; ci < G; ci += CO_NBULK) {
+                const bool ragged = cur.n < CO_T; // warp-uniform
+                for (int ci = warp - wBulk; ci < G; ci += nBulk) {
                     float* rowL = &sm.tile[slot][2 * ci][lane * CO_CH];
                     float* rowR = &sm.tile[slot][2 * ci + 1][lane * CO_CH];
                     float l[CO_CH], r[CO_CH];
@@ -516,7 +630,8 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                         l[0] = a0.x; l[1] = a0.y; l[2] = a0.z; l[3] = a0.w; l[4] = a1.x; l[5] = a1.y; l[6] = a1.z; l[7] = a1.w;
                         r[0] = b0.x; r[1] = b0.y; r[2] = b0.z; r[3] = b0.w; r[4] = b1.x; r[5] = b1.y; r[6] = b1.z; r[7] = b1.w;
                     }
-                    mask_chunk(l, r, nValid);
+                    if (ragged)
+                        mask_chunk(l, r, nValid);
                     float* monoClip = monoCta + ((size_t) ci * nSig) * 2 * CO_BLOCKMAX + blockPar * CO_BLOCKMAX + cur.off + lane * CO_CH;
                     signal_stats(l, r, sm.stats[blockPar][ci][0], firstStep, monoClip, lane, nValid);
                     for (int s = 0; s < L; ++s) {
@@ -541,7 +656,8 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                         } else if (d.kind == K_INFER) {
                             infer_chunk(l, r, d.c.infer);
                         }
-                        mask_chunk(l, r, nValid);
+                        if (ragged)
+                            mask_chunk(l, r, nValid);
                         signal_stats(l, r, sm.stats[blockPar][ci][s + 1], firstStep, monoClip + (size_t) (s + 1) * 2 * CO_BLOCKMAX,
                                      lane, nValid);
                     }
@@ -553,7 +669,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                 fence_async_smem(); // tile writes -> visible to the bulk store issued after the barrier
             }
             __syncthreads();
-            if (warp == CO_W_PRODUCER) {
+            if (isProducerWarp) {
                 for (int row = lane; row < rows; row += 32) {
                     float* dst = a.out + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.nSamples + cur.pos;
                     bulk_store(dst, &sm.tile[slot][row][0], (uint32_t) (cur.n * 4));
@@ -565,28 +681,24 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
         }
 
         // ---- epilogue: analyzers finish the last host block; everyone stores state
-        const int lastBlk = (a.nSamples + a.blockSize - 1) / a.blockSize - 1;
-        if (isAna) {
-            const int ppar = lastBlk & 1, pn = a.nSamples - lastBlk * a.blockSize;
-            const float* streams = monoCta + ((size_t) anaClip * nSig) * 2 * CO_BLOCKMAX + ppar * CO_BLOCKMAX;
-            {
-                AnaAcc acc;
-                ana_walk(ast, acc, streams + (size_t) anaSlot * 2 * CO_BLOCKMAX, pn, ana);
-                preScore = ana_finish(ast, acc, load_stats(sm.stats[ppar][anaClip][anaSlot]), pn, ana).score;
+        if (isEnvWarp || isBandWarp) {
+            const int lastBlk = (a.nSamples + a.blockSize - 1) / a.blockSize - 1;
+            const int pn = a.nSamples - lastBlk * a.blockSize;
+            analyze_pre(lastBlk, pn);
+            analyze_post(lastBlk, pn);
+            if (isAna) {
+                const long long clip = clip0 + anaClip;
+                const int b = a.slot[anaSlot].stateBase;
+                auto stv = [&](int v, float x) { a.state[(long long) (b + v) * a.clipPitch + clip] = x; };
+                if (isBandWarp) {
+                    stv(AV_LOW, ast.low); stv(AV_HIGH, ast.high);
+                } else {
+                    stv(AV_SHORT, ast.sEnv); stv(AV_LONG, ast.lEnv);
+                    stv(AV_REP_EMA, ast.repEma); stv(AV_FAT_EMA, ast.fatEma);
+                    stv(AV_COOLDOWN, __int_as_float(ast.cool));
+                    stv(AV_PRE_SCORE, preScore);
+                }
             }
-            {
-                AnaAcc acc;
-                ana_walk(ast, acc, streams + (size_t) (anaSlot + 1) * 2 * CO_BLOCKMAX, pn, ana);
-                const Metrics m = ana_finish(ast, acc, load_stats(sm.stats[ppar][anaClip][anaSlot + 1]), pn, ana);
-                publish_record(a, anaSlot, clip0 + anaClip, a.histFirstBlock + lastBlk, m, preScore, 0.0f);
-            }
-            const long long clip = clip0 + anaClip;
-            const int b = a.slot[anaSlot].stateBase;
-            auto stv = [&](int v, float x) { a.state[(long long) (b + v) * a.clipPitch + clip] = x; };
-            stv(AV_SHORT, ast.sEnv); stv(AV_LONG, ast.lEnv); stv(AV_LOW, ast.low); stv(AV_HIGH, ast.high);
-            stv(AV_REP_EMA, ast.repEma); stv(AV_FAT_EMA, ast.fatEma);
-            stv(AV_COOLDOWN, __int_as_float(ast.cool));
-            stv(AV_PRE_SCORE, preScore);
         }
         if (isScout) {
             const long long clip = clip0 + (scRow >> 1);
@@ -600,7 +712,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             a.state[(long long) (b + WV_WPOS) * a.clipPitch + clip0 + threadIdx.x] = __int_as_float(sm.widthPos[threadIdx.x]);
         }
     }
-    if (warp == CO_W_PRODUCER)
+    if (isProducerWarp)
         bulk_wait_all();
 }
 
