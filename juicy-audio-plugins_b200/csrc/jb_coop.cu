@@ -28,6 +28,7 @@
 
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -41,11 +42,12 @@ constexpr int CO_PITCH = CO_T + 4;   // floats per tile row (+16 B: row-walking 
 constexpr int CO_BLOCKMAX = 512;     // largest host block size this path takes
 constexpr int CO_MAXCHAIN = 3;       // plugins per chain on this path
 constexpr int CO_NSIG = CO_MAXCHAIN + 1;
-// Warp roles: [0] producer, [1, 2] scouts, then nAna "envelope" analyzer warps, nAna "band" analyzer
-// warps (nAna = ceil(chainLen * groupClips / 32), decided per launch), and every remaining warp is bulk.
+// Warp roles (the SM's arbiter favours high warp ids, so the longest sequential chains sit on top):
+// [0] producer, [1 .. nBulk] bulk, then 2 scouts, nAna "band" analyzer warps and, highest, nAna
+// "envelope" analyzer warps (nAna = ceil(chainLen * groupClips / 32), decided per launch).
 constexpr int CO_W_PRODUCER = 0;
-constexpr int CO_W_SCOUT = 1, CO_NSCOUT = CO_ROWS / 32; // 2 warps
-constexpr int CO_W_ANA = CO_W_SCOUT + CO_NSCOUT;
+constexpr int CO_W_BULK = 1;
+constexpr int CO_NSCOUT = CO_ROWS / 32;                 // 2 warps
 constexpr int CO_ANA_LANES = CO_GMAX * CO_MAXCHAIN;     // 96
 constexpr int CO_WARPS = 21;
 constexpr int CO_THREADS = CO_WARPS * 32;               // 672
@@ -91,18 +93,47 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-__device__ __forceinline__ void bulk_load(void* smemDst, const void* gmemSrc, uint32_t bytes, unsigned long long* bar)
+// L2 policies: the audio streams through once (evict_first) so that it does not push the analyzer
+// lanes' mono rings (evict_last), which are re-read one host block later, out to HBM.
+__device__ __forceinline__ uint64_t policy_evict_first()
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_load(void* smemDst, const void* gmemSrc, uint32_t bytes, unsigned long long* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                      smem_u32(smemDst)),
-                 "l"(gmemSrc), "r"(bytes), "r"(smem_u32(bar))
+                 "l"(gmemSrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
-__device__ __forceinline__ void bulk_store(void* gmemDst, const void* smemSrc, uint32_t bytes)
+__device__ __forceinline__ void bulk_store(void* gmemDst, const void* smemSrc, uint32_t bytes, uint64_t policy)
 {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmemDst), "r"(smem_u32(smemSrc)),
-                 "r"(bytes)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmemDst),
+                 "r"(smem_u32(smemSrc)), "r"(bytes), "l"(policy)
                  : "memory");
+}
+__device__ __forceinline__ void st_hint(float4* dst, float4 v, uint64_t policy)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+                 "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ float4 ld_hint(const float4* src, uint64_t policy)
+{
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(src), "l"(policy)
+                 : "memory");
+    return v;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -329,7 +360,7 @@ __device__ __forceinline__ void warp_sum4(float& v0, float& v1, float& v2, float
 // energy follows from mid^2 + side^2 = (l^2 + r^2) / 2 (load_stats).  The mono sum of every sample
 // goes to the analyzer lanes' scratch ring.
 __device__ __forceinline__ void signal_stats(const float (&l)[CO_CH], const float (&r)[CO_CH], float* acc, bool firstStep,
-                                             float* monoDst, int lane, int nValid)
+                                             float* monoDst, int lane, int nValid, uint64_t keep)
 {
     float mono[CO_CH];
     float rms = 0.0f, peak = 0.0f, corr = 0.0f, l2 = 0.0f, r2 = 0.0f;
@@ -344,9 +375,9 @@ __device__ __forceinline__ void signal_stats(const float (&l)[CO_CH], const floa
         r2 = fmaf(r[i], r[i], r2);
     }
     if (nValid > 0)
-        *reinterpret_cast<float4*>(monoDst) = make_float4(mono[0], mono[1], mono[2], mono[3]);
+        st_hint(reinterpret_cast<float4*>(monoDst), make_float4(mono[0], mono[1], mono[2], mono[3]), keep);
     if (nValid > 4)
-        *(reinterpret_cast<float4*>(monoDst) + 1) = make_float4(mono[4], mono[5], mono[6], mono[7]);
+        st_hint(reinterpret_cast<float4*>(monoDst) + 1, make_float4(mono[4], mono[5], mono[6], mono[7]), keep);
     warp_sum4(rms, l2, r2, corr, lane);
     peak = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(peak))); // non-negative floats order like their bits
     if (lane == 0) {
@@ -362,47 +393,95 @@ __device__ __forceinline__ void signal_stats(const float (&l)[CO_CH], const floa
 // One lane walks one analyzer's samples in order.  BANDS = false: envelopes + onset machine;
 // BANDS = true: the two band-split one-poles.  Mono samples come from the L2-resident scratch ring,
 // 16 samples (4 x 16 B) prefetched ahead.
+// Envelope lanes: the two attack/release envelopes and the onset machine over 4 samples whose
+// offsets from the group's first sample are K .. K+3 (JuicinessAnalyzer.cpp:64-75).  `rem` restates
+// onsetCooldown as "samples from the group's first until an onset is allowed again": the reference
+// decrements the counter once per sample and accepts an onset when it has reached 0, i.e. at the
+// len-th sample after the previous onset.
+template <int K>
+__device__ __forceinline__ void env_quad(AnaState& s, AnaAcc& acc, int& rem, const float4 q, const AnaCoef& c)
+{
+    const float m[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = fabsf(m[j]);
+        {
+            const bool up = a > s.sEnv;
+            s.sEnv = (up ? c.omaS : c.omrS) * a + (up ? c.aS : c.rS) * s.sEnv;
+        }
+        {
+            const bool up = a > s.lEnv;
+            s.lEnv = (up ? c.omaL : c.omrL) * a + (up ? c.aL : c.rL) * s.lEnv;
+        }
+        const float tr = fmaxf(0.0f, s.sEnv - s.lEnv);
+        acc.trAcc += tr;
+        const bool onset = (tr > 0.045f) & (rem <= K + j);
+        acc.onsets += onset ? 1 : 0;
+        rem = onset ? c.cooldownLen + (K + j) : rem;
+    }
+}
+__device__ __forceinline__ void band_quad(AnaState& s, AnaAcc& acc, const float4 q, const AnaCoef& c)
+{
+    ana_step_bands(s, acc, q.x, c);
+    ana_step_bands(s, acc, q.y, c);
+    ana_step_bands(s, acc, q.z, c);
+    ana_step_bands(s, acc, q.w, c);
+}
 template <bool BANDS>
-__device__ __forceinline__ void ana_steps4(AnaState& st, AnaAcc& acc, const float4 v, const AnaCoef& c)
+__device__ __forceinline__ void ana_group(AnaState& st, AnaAcc& acc, int& rem, const float4 q0, const float4 q1, const float4 q2,
+                                          const float4 q3, const AnaCoef& c)
 {
     if (BANDS) {
-        ana_step_bands(st, acc, v.x, c);
-        ana_step_bands(st, acc, v.y, c);
-        ana_step_bands(st, acc, v.z, c);
-        ana_step_bands(st, acc, v.w, c);
+        band_quad(st, acc, q0, c); band_quad(st, acc, q1, c); band_quad(st, acc, q2, c); band_quad(st, acc, q3, c);
     } else {
-        ana_step_env(st, acc, v.x, c);
-        ana_step_env(st, acc, v.y, c);
-        ana_step_env(st, acc, v.z, c);
-        ana_step_env(st, acc, v.w, c);
+        env_quad<0>(st, acc, rem, q0, c); env_quad<4>(st, acc, rem, q1, c);
+        env_quad<8>(st, acc, rem, q2, c); env_quad<12>(st, acc, rem, q3, c);
+        rem -= 16;
     }
 }
+
+// One lane walks one analyzer's n samples in order.  BANDS = false: envelopes + onset machine;
+// BANDS = true: the two band-split one-poles.  Mono samples come from the scratch ring in groups of
+// 16 (4 x 16 B), each group loaded two groups ahead of its use into one of three statically named
+// register buffers (no rotation copies, so a load really has two groups of work to hide behind).
+#define JB_LOAD_GROUP(B, G) do { const float4* q_ = p + 4 * (G); B##0 = ld_hint(q_, keep); B##1 = ld_hint(q_ + 1, keep); \
+                                 B##2 = ld_hint(q_ + 2, keep); B##3 = ld_hint(q_ + 3, keep); } while (0)
 template <bool BANDS>
-__device__ __forceinline__ void ana_walk(AnaState& st, AnaAcc& acc, const float* stream, int n, const AnaCoef& c)
+__device__ __forceinline__ void ana_walk(AnaState& st, AnaAcc& acc, const float* stream, int n, const AnaCoef& c, uint64_t keep)
 {
     const float4* p = reinterpret_cast<const float4*>(stream);
-    const int n4 = n >> 2;      // the path requires n % 4 == 0
-    const int nGroups = n4 >> 2; // groups of 16 samples, fetched two groups (32 samples) ahead of their use
-    float4 c0, c1, c2, c3, d0, d1, d2, d3;
-    c0 = c1 = c2 = c3 = d0 = d1 = d2 = d3 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (nGroups > 0) { c0 = p[0]; c1 = p[1]; c2 = p[2]; c3 = p[3]; }
-    if (nGroups > 1) { d0 = p[4]; d1 = p[5]; d2 = p[6]; d3 = p[7]; }
-    for (int g = 0; g < nGroups; ++g) {
-        float4 e0 = c0, e1 = c0, e2 = c0, e3 = c0;
-        if (g + 2 < nGroups) {
-            const float4* q = p + 4 * (g + 2);
-            e0 = q[0]; e1 = q[1]; e2 = q[2]; e3 = q[3];
+    const int n4 = n >> 2;       // the path requires n % 4 == 0
+    const int nGroups = n4 >> 2;
+    int rem = st.cool - 1;       // onsetCooldown -> samples until the next onset may fire (cool = 0 or 1: immediately)
+    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 a0 = z, a1 = z, a2 = z, a3 = z, b0 = z, b1 = z, b2 = z, b3 = z, c0 = z, c1 = z, c2 = z, c3 = z;
+    if (nGroups > 0) JB_LOAD_GROUP(a, 0);
+    if (nGroups > 1) JB_LOAD_GROUP(b, 1);
+    for (int g = 0; g < nGroups; g += 3) {
+        if (g + 2 < nGroups) JB_LOAD_GROUP(c, g + 2);
+        ana_group<BANDS>(st, acc, rem, a0, a1, a2, a3, c);
+        if (g + 1 < nGroups) {
+            if (g + 3 < nGroups) JB_LOAD_GROUP(a, g + 3);
+            ana_group<BANDS>(st, acc, rem, b0, b1, b2, b3, c);
         }
-        ana_steps4<BANDS>(st, acc, c0, c);
-        ana_steps4<BANDS>(st, acc, c1, c);
-        ana_steps4<BANDS>(st, acc, c2, c);
-        ana_steps4<BANDS>(st, acc, c3, c);
-        c0 = d0; c1 = d1; c2 = d2; c3 = d3;
-        d0 = e0; d1 = e1; d2 = e2; d3 = e3;
+        if (g + 2 < nGroups) {
+            if (g + 4 < nGroups) JB_LOAD_GROUP(b, g + 4);
+            ana_group<BANDS>(st, acc, rem, c0, c1, c2, c3, c);
+        }
     }
-    for (int q = 4 * nGroups; q < n4; ++q)
-        ana_steps4<BANDS>(st, acc, p[q], c);
+    if (!BANDS) // back to the reference's counter for the tail and for the state arrays
+        st.cool = max(rem + 1, 0);
+    for (int q = 4 * nGroups; q < n4; ++q) {
+        const float4 v = ld_hint(p + q, keep);
+        if (BANDS) {
+            band_quad(st, acc, v, c);
+        } else {
+            ana_step_env(st, acc, v.x, c); ana_step_env(st, acc, v.y, c);
+            ana_step_env(st, acc, v.z, c); ana_step_env(st, acc, v.w, c);
+        }
+    }
 }
+#undef JB_LOAD_GROUP
 
 __device__ __forceinline__ StatSums load_stats(const float* s)
 {
@@ -424,6 +503,7 @@ struct CoopArgs {
     float* monoScratch; // [grid][CO_GMAX][chainLen + 1][2][CO_BLOCKMAX]
     int groupClips;     // clips per group (<= CO_GMAX)
     int numGroups;
+    int debugSkip;      // profiling aid (JB_COOP_DEBUG_SKIP): bit 0 envelope walk, 1 band walk, 2 bulk math, 3 scout
 };
 
 __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_constant__ CoopArgs ca)
@@ -434,17 +514,18 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = a.chainLen;
     const int nSig = L + 1;
-    const AnaCoef ana = a.ana;
+    const AnaCoef& ana = a.ana; // stays in the kernel-parameter constant bank
 
     // roles (uniform over the launch)
     const int nAna = (L * ca.groupClips + 31) / 32;          // envelope-analyzer warps; as many band-analyzer warps
-    const int wBand = CO_W_ANA + nAna, wBulk = CO_W_ANA + 2 * nAna;
-    const int nBulk = CO_WARPS - wBulk;
+    const int wEnv = CO_WARPS - nAna, wBand = wEnv - nAna, wScout = wBand - CO_NSCOUT, wBulk = CO_W_BULK;
+    const int nBulk = wScout - wBulk;
     const bool isProducerWarp = warp == CO_W_PRODUCER;
-    const bool isScoutWarp = warp >= CO_W_SCOUT && warp < CO_W_ANA;
-    const bool isEnvWarp = warp >= CO_W_ANA && warp < wBand;
-    const bool isBandWarp = warp >= wBand && warp < wBulk;
+    const bool isScoutWarp = warp >= wScout && warp < wBand;
+    const bool isEnvWarp = warp >= wEnv;
+    const bool isBandWarp = warp >= wBand && warp < wEnv;
     const int anaThreads = 2 * nAna * 32;
+    const uint64_t polStream = policy_evict_first(), polKeep = policy_evict_last();
 
     if (threadIdx.x == 0) {
         mbar_init(&sm.bar[0], 1);
@@ -479,7 +560,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
         // ---- per-role state for this group
         // scout: Punch envelopes of row (clip, ch)
         float scF = 0.0f, scS = 0.0f;
-        const int scRow = (warp - CO_W_SCOUT) * 32 + lane;
+        const int scRow = (warp - wScout) * 32 + lane;
         const bool isScout = isScoutWarp && punchFirst && scRow < rows;
         if (isScout) {
             const long long clip = clip0 + (scRow >> 1);
@@ -488,7 +569,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             scS = a.state[(long long) (b + PV_SLOW0 + (scRow & 1)) * a.clipPitch + clip];
         }
         // analyzers: lane <-> (plugin slot, clip), once in an envelope warp and once in a band warp
-        const int anaIdx = (warp - (isBandWarp ? wBand : CO_W_ANA)) * 32 + lane;
+        const int anaIdx = (warp - (isBandWarp ? wBand : wEnv)) * 32 + lane;
         const int anaSlot = anaIdx / ca.groupClips, anaClip = anaIdx % ca.groupClips;
         const bool isAna = (isEnvWarp || isBandWarp) && anaSlot < L && anaClip < G;
         AnaState ast {};
@@ -517,13 +598,13 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             __syncwarp();
             for (int row = lane; row < rows; row += 32) {
                 const float* src = a.in + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.nSamples + c.pos;
-                bulk_load(&sm.tile[slot][row][0], src, (uint32_t) (c.n * 4), &sm.bar[slot]);
+                bulk_load(&sm.tile[slot][row][0], src, (uint32_t) (c.n * 4), &sm.bar[slot], polStream);
             }
         };
         auto scout_step = [&](const Cursor& c, unsigned step) {
             const int slot = step & 1;
             mbar_wait(&sm.bar[slot], (step >> 1) & 1);
-            if (!isScout)
+            if (!isScout || (ca.debugSkip & 8))
                 return;
             const PunchCoef& pc = a.slot[0].c.punch;
             const float4* src = reinterpret_cast<const float4*>(&sm.tile[slot][scRow][0]);
@@ -551,13 +632,13 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             ++anaCalls;
             AnaAcc acc;
             const float* stream = monoCta + ((size_t) anaClip * nSig + sig) * 2 * CO_BLOCKMAX + par * CO_BLOCKMAX;
-            if (isAna) {
+            if (isAna && !(ca.debugSkip & (isBandWarp ? 2 : 1))) {
                 if (isBandWarp) {
-                    ana_walk<true>(ast, acc, stream, n, ana);
+                    ana_walk<true>(ast, acc, stream, n, ana, polKeep);
                     sm.bandAcc[hand][anaIdx][0] = acc.lowAcc;
                     sm.bandAcc[hand][anaIdx][1] = acc.highAcc;
                 } else {
-                    ana_walk<false>(ast, acc, stream, n, ana);
+                    ana_walk<false>(ast, acc, stream, n, ana, polKeep);
                 }
             }
             named_barrier(CO_BAR_ANA, anaThreads);
@@ -620,7 +701,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                 const int nValid = max(0, min(CO_CH, cur.n - lane * CO_CH));
                 const bool firstStep = cur.off == 0;
                 const bool ragged = cur.n < CO_T; // warp-uniform
-                for (int ci = warp - wBulk; ci < G; ci += nBulk) {
+                for (int ci = warp - wBulk; ci < G && !(ca.debugSkip & 4); ci += nBulk) {
                     float* rowL = &sm.tile[slot][2 * ci][lane * CO_CH];
                     float* rowR = &sm.tile[slot][2 * ci + 1][lane * CO_CH];
                     float l[CO_CH], r[CO_CH];
@@ -633,7 +714,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                     if (ragged)
                         mask_chunk(l, r, nValid);
                     float* monoClip = monoCta + ((size_t) ci * nSig) * 2 * CO_BLOCKMAX + blockPar * CO_BLOCKMAX + cur.off + lane * CO_CH;
-                    signal_stats(l, r, sm.stats[blockPar][ci][0], firstStep, monoClip, lane, nValid);
+                    signal_stats(l, r, sm.stats[blockPar][ci][0], firstStep, monoClip, lane, nValid, polKeep);
                     for (int s = 0; s < L; ++s) {
                         const SlotDesc& d = a.slot[s];
                         if (d.kind == K_PUNCH) {
@@ -659,7 +740,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                         if (ragged)
                             mask_chunk(l, r, nValid);
                         signal_stats(l, r, sm.stats[blockPar][ci][s + 1], firstStep, monoClip + (size_t) (s + 1) * 2 * CO_BLOCKMAX,
-                                     lane, nValid);
+                                     lane, nValid, polKeep);
                     }
                     *reinterpret_cast<float4*>(rowL) = make_float4(l[0], l[1], l[2], l[3]);
                     *reinterpret_cast<float4*>(rowL + 4) = make_float4(l[4], l[5], l[6], l[7]);
@@ -672,7 +753,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             if (isProducerWarp) {
                 for (int row = lane; row < rows; row += 32) {
                     float* dst = a.out + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.nSamples + cur.pos;
-                    bulk_store(dst, &sm.tile[slot][row][0], (uint32_t) (cur.n * 4));
+                    bulk_store(dst, &sm.tile[slot][row][0], (uint32_t) (cur.n * 4), polStream);
                 }
                 bulk_commit();
             }
@@ -775,6 +856,8 @@ int jbk_launch_coop(const ProcArgs* args, float* monoScratch, int numSMs, void* 
         g = CO_GMAX;
     ca.groupClips = g;
     ca.numGroups = (args->nClips + g - 1) / g;
+    const char* dbg = getenv("JB_COOP_DEBUG_SKIP");
+    ca.debugSkip = dbg ? atoi(dbg) : 0;
     const int grid = ca.numGroups < numSMs ? ca.numGroups : numSMs;
     jb_coop_kernel<<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
     jbk_note_launch();
