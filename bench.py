@@ -47,6 +47,13 @@ def load_juicy_batch():
     return mod
 
 
+def load_sharding():
+    spec = importlib.util.spec_from_file_location("jb_sharding", os.path.join(PKG, "sharding.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -241,6 +248,7 @@ def run_engine_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     jb = load_juicy_batch()
+    sharding = load_sharding()
     n_clips, n = args.clips, args.samples
     count = n_clips * 2 * n
     d_in = torch.empty(count, dtype=torch.float32, device="cuda")
@@ -254,14 +262,15 @@ def run_engine_arm(args):
     last_slot = len(CHAIN) - 1
     rec_bytes = 16 * 4 * n_clips
     # device view of the engine's SoA metrics record [16][clipPitch] for the gather
-    pitch = (n_clips + 31) // 32 * 32
+    pitch = sharding.clip_pitch(n_clips)
 
     class _DeviceView:  # zero-copy torch view of the engine's record block (plumbing for the NCCL gather)
         __cuda_array_interface__ = {"shape": (16 * pitch,), "typestr": "<f4", "version": 2,
                                     "data": (eng.metrics_device_ptr(last_slot), False)}
 
     local_rec = torch.as_tensor(_DeviceView(), device="cuda")
-    gathered = torch.empty(world * 16 * pitch, dtype=torch.float32, device="cuda") if world > 1 else None
+    first_clip, _ = sharding.shard_range(world * n_clips, rank, world)  # weak scaling: n_clips per rank
+    assert first_clip == rank * n_clips
 
     def barrier():
         if world > 1:
@@ -272,7 +281,7 @@ def run_engine_arm(args):
         eng.process_device(d_in.data_ptr(), d_out.data_ptr(), n)
         if world > 1:
             # per-clip records -> every rank (north_star: NCCL only to gather per-clip scores)
-            dist.all_gather_into_tensor(gathered, local_rec)
+            sharding.gather_records(local_rec, world, dist)
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):

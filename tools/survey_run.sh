@@ -1,0 +1,16 @@
+set -x
+CB="python tools/chain_bench.py --steps 2 --warmup 1"
+$CB --chain JuicyInfer --clips 65536 --synth mixed --path lane
+$CB --chain JuicyInfer --clips 16384 --synth mixed --path lane
+$CB --chain JuicyInfer --clips 16384 --synth mixed --path coop
+$CB --chain JuicyWidth --clips 16384 --synth drum --path lane
+$CB --chain JuicyWidth --clips 16384 --synth drum --path coop
+$CB --chain JuicySaturator --clips 16384 --synth sweep --path lane
+$CB --chain JuicyCohere --clips 16384 --synth noise --path lane
+$CB --chain JuicyPunch --clips 16384 --synth drum --path lane
+$CB --chain JuicyPunch --clips 16384 --synth drum --path coop
+$CB --chain JuicyMotion --clips 16384 --synth drum --path lane
+for m in 0 1 2 3 4; do $CB --chain JuicyTexture --clips 8192 --synth impulse --path lane --param 0:material=$m; done
+$CB --chain JuicyPunch,JuicySaturator,JuicyTexture,JuicyWidth,JuicyMotion,JuicyCohere,JuicyInfer --clips 32768 --synth mixed --path lane
+$CB --chain JuicyPunch,JuicyWidth --clips 4096 --synth drum --path lane
+$CB --chain JuicyPunch,JuicyWidth --clips 32768 --synth drum --path lane
