@@ -393,13 +393,12 @@ __device__ __forceinline__ void signal_stats(const float (&l)[CO_CH], const floa
 // One lane walks one analyzer's samples in order.  BANDS = false: envelopes + onset machine;
 // BANDS = true: the two band-split one-poles.  Mono samples come from the L2-resident scratch ring,
 // 16 samples (4 x 16 B) prefetched ahead.
-// Envelope lanes: the two attack/release envelopes and the onset machine over 4 samples whose
-// offsets from the group's first sample are K .. K+3 (JuicinessAnalyzer.cpp:64-75).  `rem` restates
-// onsetCooldown as "samples from the group's first until an onset is allowed again": the reference
-// decrements the counter once per sample and accepts an onset when it has reached 0, i.e. at the
-// len-th sample after the previous onset.
-template <int K>
-__device__ __forceinline__ void env_quad(AnaState& s, AnaAcc& acc, int& rem, const float4 q, const AnaCoef& c)
+// Envelope lanes: the two attack/release envelopes (updateEnvelope, JuicinessAnalyzer.cpp:24-29,64-65),
+// the transient sum (:66-67) and the largest transient of the group, over 4 samples.  The onset
+// machine (:69-75) is not stepped per sample: a group of 16 can hold an onset only if its largest
+// transient exceeds the threshold while the cooldown allows one, and only then is it replayed
+// sample by sample (onset_replay) -- same decisions, a fraction of the instructions.
+__device__ __forceinline__ void env_quad(AnaState& s, float& trAcc, float& gmax, const float4 q, const AnaCoef& c)
 {
     const float m[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
@@ -414,18 +413,48 @@ __device__ __forceinline__ void env_quad(AnaState& s, AnaAcc& acc, int& rem, con
             s.lEnv = (up ? c.omaL : c.omrL) * a + (up ? c.aL : c.rL) * s.lEnv;
         }
         const float tr = fmaxf(0.0f, s.sEnv - s.lEnv);
-        acc.trAcc += tr;
-        const bool onset = (tr > 0.045f) & (rem <= K + j);
-        acc.onsets += onset ? 1 : 0;
-        rem = onset ? c.cooldownLen + (K + j) : rem;
+        trAcc += tr;
+        gmax = fmaxf(gmax, tr);
     }
 }
+// `rem` restates onsetCooldown as "samples from the group's first until an onset is allowed again":
+// the reference decrements the counter once per sample and accepts an onset when it has reached 0,
+// i.e. at the len-th sample after the previous onset.  Replays the group's 16 samples from the
+// envelope state at its start (sEnv0, lEnv0) and applies the onset decisions.
+__device__ __noinline__ void onset_replay(float sEnv, float lEnv, int& rem, int& onsets, const float4 q0, const float4 q1,
+                                          const float4 q2, const float4 q3, const AnaCoef& c)
+{
+    const float m[16] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w };
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float a = fabsf(m[j]);
+        {
+            const bool up = a > sEnv;
+            sEnv = (up ? c.omaS : c.omrS) * a + (up ? c.aS : c.rS) * sEnv;
+        }
+        {
+            const bool up = a > lEnv;
+            lEnv = (up ? c.omaL : c.omrL) * a + (up ? c.aL : c.rL) * lEnv;
+        }
+        const float tr = fmaxf(0.0f, sEnv - lEnv);
+        const bool onset = (tr > 0.045f) & (rem <= j);
+        onsets += onset ? 1 : 0;
+        rem = onset ? c.cooldownLen + j : rem;
+    }
+}
+// Band lanes: the two band-split one-poles in the reference's order (:79-82); their energies (:83-84)
+// are plain sums feeding continuous features, accumulated with fused multiply-adds.
 __device__ __forceinline__ void band_quad(AnaState& s, AnaAcc& acc, const float4 q, const AnaCoef& c)
 {
-    ana_step_bands(s, acc, q.x, c);
-    ana_step_bands(s, acc, q.y, c);
-    ana_step_bands(s, acc, q.z, c);
-    ana_step_bands(s, acc, q.w, c);
+    const float m[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s.low += c.lowCoeff * (m[j] - s.low);
+        s.high += c.highCoeff * (m[j] - s.high);
+        const float hi = m[j] - s.high;
+        acc.lowAcc = fmaf(s.low, s.low, acc.lowAcc);
+        acc.highAcc = fmaf(hi, hi, acc.highAcc);
+    }
 }
 template <bool BANDS>
 __device__ __forceinline__ void ana_group(AnaState& st, AnaAcc& acc, int& rem, const float4 q0, const float4 q1, const float4 q2,
@@ -434,8 +463,12 @@ __device__ __forceinline__ void ana_group(AnaState& st, AnaAcc& acc, int& rem, c
     if (BANDS) {
         band_quad(st, acc, q0, c); band_quad(st, acc, q1, c); band_quad(st, acc, q2, c); band_quad(st, acc, q3, c);
     } else {
-        env_quad<0>(st, acc, rem, q0, c); env_quad<4>(st, acc, rem, q1, c);
-        env_quad<8>(st, acc, rem, q2, c); env_quad<12>(st, acc, rem, q3, c);
+        const float sEnv0 = st.sEnv, lEnv0 = st.lEnv;
+        float gmax = 0.0f;
+        env_quad(st, acc.trAcc, gmax, q0, c); env_quad(st, acc.trAcc, gmax, q1, c);
+        env_quad(st, acc.trAcc, gmax, q2, c); env_quad(st, acc.trAcc, gmax, q3, c);
+        if (gmax > 0.045f && rem <= 15)
+            onset_replay(sEnv0, lEnv0, rem, acc.onsets, q0, q1, q2, q3, c);
         rem -= 16;
     }
 }
@@ -597,7 +630,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                 mbar_expect_tx(&sm.bar[slot], (uint32_t) (rows * c.n * 4));
             __syncwarp();
             for (int row = lane; row < rows; row += 32) {
-                const float* src = a.in + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.nSamples + c.pos;
+                const float* src = a.in + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.rowPitch + c.pos;
                 bulk_load(&sm.tile[slot][row][0], src, (uint32_t) (c.n * 4), &sm.bar[slot], polStream);
             }
         };
@@ -632,6 +665,8 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             ++anaCalls;
             AnaAcc acc;
             const float* stream = monoCta + ((size_t) anaClip * nSig + sig) * 2 * CO_BLOCKMAX + par * CO_BLOCKMAX;
+            if (ca.debugSkip & 16) // probe: every walk re-reads one L1-resident kilobyte per lane
+                stream = monoCta + (size_t) anaIdx * 256;
             if (isAna && !(ca.debugSkip & (isBandWarp ? 2 : 1))) {
                 if (isBandWarp) {
                     ana_walk<true>(ast, acc, stream, n, ana, polKeep);
@@ -643,7 +678,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             }
             named_barrier(CO_BAR_ANA, anaThreads);
             Metrics m {};
-            if (isAna && isEnvWarp) {
+            if (isAna && isEnvWarp && !(ca.debugSkip & 32)) {
                 acc.lowAcc = sm.bandAcc[hand][anaIdx][0];
                 acc.highAcc = sm.bandAcc[hand][anaIdx][1];
                 m = ana_finish(ast, acc, load_stats(sm.stats[par][anaClip][sig]), n, ana);
@@ -752,7 +787,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             __syncthreads();
             if (isProducerWarp) {
                 for (int row = lane; row < rows; row += 32) {
-                    float* dst = a.out + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.nSamples + cur.pos;
+                    float* dst = a.out + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.rowPitch + cur.pos;
                     bulk_store(dst, &sm.tile[slot][row][0], (uint32_t) (cur.n * 4), polStream);
                 }
                 bulk_commit();
@@ -817,7 +852,7 @@ int jbk_coop_supported(const ProcArgs* a)
 {
     if (a->chainLen < 1 || a->chainLen > CO_MAXCHAIN || a->nCh != 2)
         return 0;
-    if (a->blockSize > CO_BLOCKMAX || a->blockSize % 4 != 0 || a->nSamples % 4 != 0)
+    if (a->blockSize > CO_BLOCKMAX || a->blockSize % 4 != 0 || a->nSamples % 4 != 0 || a->rowPitch % 4 != 0)
         return 0;
     if (((uintptr_t) a->in | (uintptr_t) a->out) & 15u)
         return 0;

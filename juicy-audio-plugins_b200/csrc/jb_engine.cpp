@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -106,6 +107,7 @@ struct jb_engine {
     // jb_process_host staging
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
     float* dStage[3] = { nullptr, nullptr, nullptr };
+    std::vector<cudaEvent_t> sliceEvents;
     cudaEvent_t evIn[3] = {}, evDone[3] = {}, evOut[3] = {};
     size_t stageBytes = 0;
 
@@ -171,6 +173,9 @@ void freeDevice(jb_engine* e)
     for (cudaEvent_t ev : e->timingEvents)
         cudaEventDestroy(ev);
     e->timingEvents.clear();
+    for (cudaEvent_t ev : e->sliceEvents)
+        cudaEventDestroy(ev);
+    e->sliceEvents.clear();
     e->timingUsed = 0;
     if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
     e->stream = nullptr;
@@ -263,7 +268,8 @@ int resetState(jb_engine* e)
     return JB_OK;
 }
 
-int buildArgs(jb_engine* e, ProcArgs& a, const float* dIn, float* dOut, int nSamples, int nClips, long long clipOffset)
+int buildArgs(jb_engine* e, ProcArgs& a, const float* dIn, float* dOut, int nSamples, int nClips, long long clipOffset,
+              long long rowPitch = 0)
 {
     std::memset(&a, 0, sizeof a);
     a.in = dIn;
@@ -279,12 +285,13 @@ int buildArgs(jb_engine* e, ProcArgs& a, const float* dIn, float* dOut, int nSam
     a.nClips = nClips;
     a.nCh = e->nCh;
     a.nSamples = nSamples;
+    a.rowPitch = rowPitch > 0 ? rowPitch : nSamples;
     a.blockSize = e->blockSize;
     a.histFirstBlock = (int) std::min<long long>(e->blocksDone, 0x7fffffff);
     a.histMaxBlocks = e->histMaxBlocks;
     a.chainLen = (int) e->chain.size();
     const bool aligned = ((reinterpret_cast<uintptr_t>(dIn) | reinterpret_cast<uintptr_t>(dOut)) & 15u) == 0;
-    a.vecOk = (aligned && nSamples % 4 == 0 && e->blockSize % 4 == 0) ? 1 : 0;
+    a.vecOk = (aligned && nSamples % 4 == 0 && a.rowPitch % 4 == 0 && e->blockSize % 4 == 0) ? 1 : 0;
     a.ana = jb::makeAnaCoef(e->sampleRate);
     for (size_t s = 0; s < e->chain.size(); ++s) {
         a.slot[s].kind = e->chain[s];
@@ -641,57 +648,91 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
     if (n_samples <= 0)
         return n_samples == 0 ? JB_OK : fail(JB_ERR_ARG, "jb_process_host: negative n_samples");
 
-    // Clip ranges stream through three device buffers: upload (copyIn stream),
-    // render (engine stream), download (copyOut stream), chained by events, so the
-    // PCIe transfers of neighbouring ranges overlap the kernel.
-    const size_t clipBytes = sizeof(float) * (size_t) e->nCh * (size_t) n_samples;
-    long long chunkClips = std::max<long long>(32, (long long) ((size_t) 256 << 20) / (long long) clipBytes / 32 * 32);
-    chunkClips = std::min<long long>(chunkClips, e->clipPitch);
-    const size_t need = clipBytes * (size_t) chunkClips;
+    // Time-sliced streaming.  The batch lives in one device buffer with the caller's layout
+    // [clip][channel][sample]; the render is cut along TIME into slices of whole host blocks, and three
+    // streams overlap slice i+1's upload, slice i's render and slice i-1's download (2-D copies: one row per
+    // (clip, channel), the slice's samples wide).  Cutting along time keeps every launch as wide as the
+    // whole batch (all SMs busy, the per-clip sequential recurrences only a slice long per launch) and is
+    // exact: state carries across launches like across consecutive host callbacks.  Batches larger than the
+    // pass budget are additionally cut into clip ranges ("passes"), two device buffers alternating.
+    const size_t rowBytes = sizeof(float) * (size_t) n_samples;
+    const size_t clipBytes = rowBytes * (size_t) e->nCh;
+    auto envMiB = [](const char* name, size_t dflt) {
+        const char* v = std::getenv(name);
+        return (size_t) (v ? std::max(1, std::atoi(v)) : (int) dflt) << 20;
+    };
+    const size_t passBudget = envMiB("JB_HOST_PASS_MIB", 8192), sliceTarget = envMiB("JB_HOST_SLICE_MIB", 96);
+    long long passClips = std::max<long long>(32, (long long) (passBudget / clipBytes) / 32 * 32);
+    passClips = std::min<long long>(passClips, e->nClips);
+    const int nPasses = (int) ((e->nClips + passClips - 1) / passClips);
+    const int totalBlocks = (n_samples + e->blockSize - 1) / e->blockSize;
+    const size_t blockBytesAllClips = sizeof(float) * (size_t) e->blockSize * (size_t) e->nCh * (size_t) passClips;
+    int sliceBlocks = (int) std::max<size_t>(1, sliceTarget / std::max<size_t>(1, blockBytesAllClips));
+    sliceBlocks = std::min(sliceBlocks, totalBlocks);
+    const int nSlices = (totalBlocks + sliceBlocks - 1) / sliceBlocks;
+
     if (e->copyIn == nullptr) {
         JB_CUDA(cudaStreamCreateWithFlags(&e->copyIn, cudaStreamNonBlocking));
         JB_CUDA(cudaStreamCreateWithFlags(&e->copyOut, cudaStreamNonBlocking));
-        for (int i = 0; i < 3; ++i) {
-            JB_CUDA(cudaEventCreateWithFlags(&e->evIn[i], cudaEventDisableTiming));
-            JB_CUDA(cudaEventCreateWithFlags(&e->evDone[i], cudaEventDisableTiming));
+        for (int i = 0; i < 3; ++i)
             JB_CUDA(cudaEventCreateWithFlags(&e->evOut[i], cudaEventDisableTiming));
-        }
     }
-    if (need > e->stageBytes) {
-        for (int i = 0; i < 3; ++i) {
+    const size_t need = clipBytes * (size_t) passClips;
+    const int nBuffers = nPasses > 1 ? 2 : 1;
+    for (int i = 0; i < nBuffers; ++i) {
+        if (e->dStage[i] == nullptr || need > e->stageBytes) {
             cudaFree(e->dStage[i]);
             e->dStage[i] = nullptr;
             JB_CUDA(cudaMalloc(&e->dStage[i], need));
         }
-        e->stageBytes = need;
     }
+    e->stageBytes = std::max(e->stageBytes, need);
+    while (e->sliceEvents.size() < (size_t) 2 * (size_t) nSlices) {
+        cudaEvent_t ev = nullptr;
+        JB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->sliceEvents.push_back(ev);
+    }
+
+    const long long blocksBase = e->blocksDone;
     int rcLaunch = JB_OK;
-    int chunkIndex = 0;
-    for (long long c0 = 0; c0 < e->nClips; c0 += chunkClips, ++chunkIndex) {
-        const int b = chunkIndex % 3;
-        const int nc = (int) std::min<long long>(chunkClips, e->nClips - c0);
-        if (chunkIndex >= 3)
-            JB_CUDA(cudaStreamWaitEvent(e->copyIn, e->evOut[b], 0)); // buffer b's previous download finished
-        JB_CUDA(cudaMemcpyAsync(e->dStage[b], h_in + (size_t) c0 * e->nCh * n_samples, clipBytes * (size_t) nc,
-                                cudaMemcpyHostToDevice, e->copyIn));
-        JB_CUDA(cudaEventRecord(e->evIn[b], e->copyIn));
-        JB_CUDA(cudaStreamWaitEvent(e->stream, e->evIn[b], 0));
-        ProcArgs a;
-        buildArgs(e, a, e->dStage[b], e->dStage[b], n_samples, nc, c0);
-        if ((rcLaunch = launchProcess(e, a)) != JB_OK)
-            break;
-        JB_CUDA(cudaEventRecord(e->evDone[b], e->stream));
-        JB_CUDA(cudaStreamWaitEvent(e->copyOut, e->evDone[b], 0));
-        JB_CUDA(cudaMemcpyAsync(h_out + (size_t) c0 * e->nCh * n_samples, e->dStage[b], clipBytes * (size_t) nc,
-                                cudaMemcpyDeviceToHost, e->copyOut));
-        JB_CUDA(cudaEventRecord(e->evOut[b], e->copyOut));
+    for (int pass = 0; pass < nPasses && rcLaunch == JB_OK; ++pass) {
+        const long long c0 = (long long) pass * passClips;
+        const int nc = (int) std::min<long long>(passClips, e->nClips - c0);
+        float* dBuf = e->dStage[pass % nBuffers];
+        const size_t rows = (size_t) nc * (size_t) e->nCh;
+        const float* hIn = h_in + (size_t) c0 * e->nCh * n_samples;
+        float* hOut = h_out + (size_t) c0 * e->nCh * n_samples;
+        if (pass >= nBuffers) // this buffer's previous pass has been downloaded
+            JB_CUDA(cudaStreamWaitEvent(e->copyIn, e->evOut[pass % nBuffers], 0));
+        for (int sl = 0; sl < nSlices; ++sl) {
+            const int firstBlock = sl * sliceBlocks;
+            const int t0 = firstBlock * e->blockSize;
+            const int ns = std::min(n_samples - t0, sliceBlocks * e->blockSize);
+            cudaEvent_t evIn = e->sliceEvents[(size_t) 2 * sl], evDone = e->sliceEvents[(size_t) 2 * sl + 1];
+            JB_CUDA(cudaMemcpy2DAsync(dBuf + t0, rowBytes, hIn + t0, rowBytes, sizeof(float) * (size_t) ns, rows,
+                                      cudaMemcpyHostToDevice, e->copyIn));
+            JB_CUDA(cudaEventRecord(evIn, e->copyIn));
+            JB_CUDA(cudaStreamWaitEvent(e->stream, evIn, 0));
+            ProcArgs a;
+            e->blocksDone = blocksBase + firstBlock; // history index of the slice's first block
+            buildArgs(e, a, dBuf + t0, dBuf + t0, ns, nc, c0, n_samples);
+            if ((rcLaunch = launchProcess(e, a)) != JB_OK)
+                break;
+            JB_CUDA(cudaEventRecord(evDone, e->stream));
+            JB_CUDA(cudaStreamWaitEvent(e->copyOut, evDone, 0));
+            JB_CUDA(cudaMemcpy2DAsync(hOut + t0, rowBytes, dBuf + t0, rowBytes, sizeof(float) * (size_t) ns, rows,
+                                      cudaMemcpyDeviceToHost, e->copyOut));
+        }
+        JB_CUDA(cudaEventRecord(e->evOut[pass % nBuffers], e->copyOut));
+        // (the slice events are re-recorded by the next pass; the waits above captured this pass's records)
     }
     JB_CUDA(cudaStreamSynchronize(e->copyIn));
     JB_CUDA(cudaStreamSynchronize(e->stream));
     JB_CUDA(cudaStreamSynchronize(e->copyOut));
+    e->blocksDone = blocksBase;
     if (rcLaunch != JB_OK)
         return rcLaunch;
-    e->blocksDone += (n_samples + e->blockSize - 1) / e->blockSize;
+    e->blocksDone += totalBlocks;
     return JB_OK;
 }
 

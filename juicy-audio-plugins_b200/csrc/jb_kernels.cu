@@ -783,8 +783,8 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
     const Lane L { a, clip };
     const int preSlot = mainSlot + 1;
     const bool firstRead = mainSlot <= 0; // sweep 0 and plugin 0's sweep read the caller's input
-    const long long rowL = (clip * a.nCh) * (long long) a.nSamples + pos;
-    const long long rowR = rowL + a.nSamples;
+    const long long rowL = (clip * a.nCh) * a.rowPitch + pos;
+    const long long rowR = rowL + a.rowPitch;
     const float* srcL = (firstRead ? a.in : a.out) + rowL;
     const float* srcR = (firstRead ? a.in : a.out) + rowR;
     float* dstL = a.out + rowL;

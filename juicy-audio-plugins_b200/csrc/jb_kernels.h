@@ -146,6 +146,8 @@ struct ProcArgs {
     long long ringClipStride, ringTimeStride; // time-major [ringLen][clipPitch] (1, clipPitch) or clip-major [clip][ringLen] (ringLen, 1)
     float* texWave;        // [2][waveSize][clipPitch]  (Texture waveguides)
     long long clipPitch;
+    long long rowPitch;    // samples between consecutive (clip, channel) rows of in / out (>= nSamples; a call may
+                           // render a time slice [t0, t0 + nSamples) of longer clips, in/out already offset by t0)
     int nClips, nCh, nSamples, blockSize;
     int histFirstBlock, histMaxBlocks;
     int chainLen;

@@ -268,3 +268,33 @@ def test_coop_kernel_many_groups(jb, port):
     ref, hists = oracle_render(port, chain, clips[pick])
     assert_samples_close(outs["coop"][0][pick], ref, "coop vs oracle, many groups")
     assert_records_close(outs["coop"][2][pick], np.stack([h[1][-1] for h in hists]), "many groups records")
+
+
+def test_host_streaming_slices_and_passes_are_exact(jb, monkeypatch):
+    """jb_process_host cuts the render into time slices (whole host blocks) and, for big batches, clip
+    passes; any cut must give the bits of the uncut render (state carries like across host callbacks)."""
+    chain = ["JuicyPunch", "JuicyWidth", "JuicyInfer"]
+    n_clips, n = 96, 9 * BLOCK + 100
+    clips = jb.synth_clips("mixed", 3, n_clips, n)
+
+    def render(env):
+        for k in ("JB_HOST_PASS_MIB", "JB_HOST_SLICE_MIB"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = jb.BatchProcessor(chain, n_clips)
+        eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+        eng.enableHistory(16)
+        out = eng.processBlock(clips)
+        hist = [eng.getHistory(s) for s in range(len(chain))]
+        launches = sum(eng.path_launches())
+        eng.close()
+        return out, hist, launches
+
+    whole, hist_whole, one = render({"JB_HOST_SLICE_MIB": "4096"})
+    assert one == 1
+    sliced, hist_sliced, many = render({"JB_HOST_SLICE_MIB": "1", "JB_HOST_PASS_MIB": "1"})  # 1 MiB: 2 blocks x 32 clips
+    assert many > 4
+    assert np.array_equal(whole, sliced)
+    for a, b in zip(hist_whole, hist_sliced):
+        assert a.shape == b.shape and np.array_equal(a, b)
