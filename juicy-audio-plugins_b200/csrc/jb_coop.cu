@@ -49,11 +49,13 @@ constexpr int CO_W_PRODUCER = 0;
 constexpr int CO_W_BULK = 1;
 constexpr int CO_NSCOUT = CO_ROWS / 32;                 // 2 warps
 constexpr int CO_ANA_LANES = CO_GMAX * CO_MAXCHAIN;     // 96
-constexpr int CO_WARPS = 21;
+constexpr int CO_WARPS = 20;
 constexpr int CO_THREADS = CO_WARPS * 32;               // 672
 constexpr int CO_BAR_ANA = 1;                           // named barrier of the analyzer warps
 
 struct CoopSmem {
+    // first, so that every 256-byte row is 256-byte aligned (the swizzle xors address bits 4..7)
+    float4 anaRing[2][CO_ANA_LANES][16];        //  49,152 B  per analyzer lane (envelope / band role): 64 mono samples in flight
     float tile[2][CO_ROWS][CO_PITCH];           // 133,120 B
     float2 ckpt[2][CO_ROWS][CO_T / CO_CH];      //  32,768 B  Punch (fast, slow) at every chunk start
     float stats[2][CO_GMAX][CO_NSIG][8];        //   8,192 B  sum m^2, peak, sum l^2, sum r^2, sum l*r per (block parity, clip, signal)
@@ -395,7 +397,7 @@ __device__ __forceinline__ void signal_stats(const float (&l)[CO_CH], const floa
 // 16 samples (4 x 16 B) prefetched ahead.
 // Envelope lanes: the two attack/release envelopes (updateEnvelope, JuicinessAnalyzer.cpp:24-29,64-65),
 // the transient sum (:66-67) and the largest transient of the group, over 4 samples.  The onset
-// machine (:69-75) is not stepped per sample: a group of 16 can hold an onset only if its largest
+// machine (:69-75) is not stepped per sample: a group of 8 can hold an onset only if its largest
 // transient exceeds the threshold while the cooldown allows one, and only then is it replayed
 // sample by sample (onset_replay) -- same decisions, a fraction of the instructions.
 __device__ __forceinline__ void env_quad(AnaState& s, float& trAcc, float& gmax, const float4 q, const AnaCoef& c)
@@ -419,14 +421,14 @@ __device__ __forceinline__ void env_quad(AnaState& s, float& trAcc, float& gmax,
 }
 // `rem` restates onsetCooldown as "samples from the group's first until an onset is allowed again":
 // the reference decrements the counter once per sample and accepts an onset when it has reached 0,
-// i.e. at the len-th sample after the previous onset.  Replays the group's 16 samples from the
-// envelope state at its start (sEnv0, lEnv0) and applies the onset decisions.
+// i.e. at the len-th sample after the previous onset.  Replays the group's 8 samples from the
+// envelope state at its start (sEnv, lEnv) and applies the onset decisions.  Rare (once per onset).
 __device__ __noinline__ void onset_replay(float sEnv, float lEnv, int& rem, int& onsets, const float4 q0, const float4 q1,
-                                          const float4 q2, const float4 q3, const AnaCoef& c)
+                                          const AnaCoef& c)
 {
-    const float m[16] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w };
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    const float m[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
         const float a = fabsf(m[j]);
         {
             const bool up = a > sEnv;
@@ -456,56 +458,103 @@ __device__ __forceinline__ void band_quad(AnaState& s, AnaAcc& acc, const float4
         acc.highAcc = fmaf(hi, hi, acc.highAcc);
     }
 }
+// 8 samples of one analyzer lane
 template <bool BANDS>
-__device__ __forceinline__ void ana_group(AnaState& st, AnaAcc& acc, int& rem, const float4 q0, const float4 q1, const float4 q2,
-                                          const float4 q3, const AnaCoef& c)
+__device__ __forceinline__ void ana_group(AnaState& st, AnaAcc& acc, int& rem, const float4 q0, const float4 q1, const AnaCoef& c)
 {
     if (BANDS) {
-        band_quad(st, acc, q0, c); band_quad(st, acc, q1, c); band_quad(st, acc, q2, c); band_quad(st, acc, q3, c);
+        band_quad(st, acc, q0, c); band_quad(st, acc, q1, c);
     } else {
         const float sEnv0 = st.sEnv, lEnv0 = st.lEnv;
         float gmax = 0.0f;
         env_quad(st, acc.trAcc, gmax, q0, c); env_quad(st, acc.trAcc, gmax, q1, c);
-        env_quad(st, acc.trAcc, gmax, q2, c); env_quad(st, acc.trAcc, gmax, q3, c);
-        if (gmax > 0.045f && rem <= 15)
-            onset_replay(sEnv0, lEnv0, rem, acc.onsets, q0, q1, q2, q3, c);
-        rem -= 16;
+        if (gmax > 0.045f && rem <= 7)
+            onset_replay(sEnv0, lEnv0, rem, acc.onsets, q0, q1, c);
+        rem -= 8;
     }
 }
 
 // One lane walks one analyzer's n samples in order.  BANDS = false: envelopes + onset machine;
-// BANDS = true: the two band-split one-poles.  Mono samples come from the scratch ring in groups of
-// 16 (4 x 16 B), each group loaded two groups ahead of its use into one of three statically named
-// register buffers (no rotation copies, so a load really has two groups of work to hide behind).
-#define JB_LOAD_GROUP(B, G) do { const float4* q_ = p + 4 * (G); B##0 = ld_hint(q_, keep); B##1 = ld_hint(q_ + 1, keep); \
-                                 B##2 = ld_hint(q_ + 2, keep); B##3 = ld_hint(q_ + 3, keep); } while (0)
-template <bool BANDS>
-__device__ __forceinline__ void ana_walk(AnaState& st, AnaAcc& acc, const float* stream, int n, const AnaCoef& c, uint64_t keep)
+// BANDS = true: the two band-split one-poles.  The lane's mono stream lies in the L2-resident scratch
+// ring; the lane copies it asynchronously (cp.async, 16 B pieces, no register landing, no scoreboard
+// wait) into its own 64-sample row of shared memory 48 samples ahead of use, and reads it back one
+// 8-sample group ahead -- so neither L2/HBM latency nor the shared-memory load sits on the
+// recurrence.  The loop body is kept to 16 samples: with five roles running different code on one SM
+// the instruction caches, not the issue slots, were the first limit (profiles/r01_v4_*).
+// Piece k of a row is stored at k ^ (lane & 7): the 8 lanes of a quarter-warp reading the same piece
+// hit 8 different 16-byte bank groups.
+__device__ __forceinline__ void cp_async16(uint32_t smemDst, const void* gmemSrc, uint64_t policy)
 {
-    const float4* p = reinterpret_cast<const float4*>(stream);
-    const int n4 = n >> 2;       // the path requires n % 4 == 0
-    const int nGroups = n4 >> 2;
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smemDst), "l"(gmemSrc), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int CO_FEED_AHEAD = 6; // groups of 8 samples in flight per lane (ring of 8 groups)
+constexpr int CO_FEED_PAD = 8 * (CO_FEED_AHEAD + 2); // floats a walk may copy (never use) past its stream's end
+
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+struct AnaFeed {
+    const float* stream; // global: this lane's mono samples of the call
+    uint32_t laneBase;   // shared: address of this lane's 256-byte ring row, xor 16 * (lane & 7) (the swizzle)
+    uint64_t policy;
+    // group g -> ring pieces 2 (g & 7), +1.  Unconditional: groups past the call's end copy scratch that is never used.
+    __device__ __forceinline__ void issue(int g) const
+    {
+        const float* src = stream + 8 * g;
+        const uint32_t off = (uint32_t) (g & 7) << 5;
+        cp_async16(laneBase ^ off, src, policy);
+        cp_async16(laneBase ^ (off | 16u), src + 4, policy);
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void read(int g, float4& q0, float4& q1) const
+    {
+        const uint32_t off = (uint32_t) (g & 7) << 5;
+        q0 = lds128(laneBase ^ off);
+        q1 = lds128(laneBase ^ (off | 16u));
+    }
+};
+
+template <bool BANDS>
+__device__ __forceinline__ void ana_walk(AnaState& st, AnaAcc& acc, const AnaFeed& f, int n, const AnaCoef& c)
+{
+    const int nGroups = n >> 3;  // the path requires n % 4 == 0
+    const int nPairs = nGroups >> 1;
     int rem = st.cool - 1;       // onsetCooldown -> samples until the next onset may fire (cool = 0 or 1: immediately)
-    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float4 a0 = z, a1 = z, a2 = z, a3 = z, b0 = z, b1 = z, b2 = z, b3 = z, c0 = z, c1 = z, c2 = z, c3 = z;
-    if (nGroups > 0) JB_LOAD_GROUP(a, 0);
-    if (nGroups > 1) JB_LOAD_GROUP(b, 1);
-    for (int g = 0; g < nGroups; g += 3) {
-        if (g + 2 < nGroups) JB_LOAD_GROUP(c, g + 2);
-        ana_group<BANDS>(st, acc, rem, a0, a1, a2, a3, c);
-        if (g + 1 < nGroups) {
-            if (g + 3 < nGroups) JB_LOAD_GROUP(a, g + 3);
-            ana_group<BANDS>(st, acc, rem, b0, b1, b2, b3, c);
-        }
-        if (g + 2 < nGroups) {
-            if (g + 4 < nGroups) JB_LOAD_GROUP(b, g + 4);
-            ana_group<BANDS>(st, acc, rem, c0, c1, c2, c3, c);
-        }
+    float4 a0, a1, b0, b1;
+#pragma unroll
+    for (int g = 0; g < CO_FEED_AHEAD; ++g)
+        f.issue(g);
+    cp_async_wait<CO_FEED_AHEAD - 1>(); // group 0 has landed
+    f.read(0, a0, a1);
+    int g = 0;
+#pragma unroll 1
+    for (int pr = 0; pr < nPairs; ++pr, g += 2) { // 16 samples per trip, no conditions but the trip count
+        f.issue(g + CO_FEED_AHEAD);          // its slot held group g - 2 (consumed)
+        cp_async_wait<CO_FEED_AHEAD - 1>();  // groups <= g + 1 have landed
+        f.read(g + 1, b0, b1);
+        ana_group<BANDS>(st, acc, rem, a0, a1, c);
+        f.issue(g + 1 + CO_FEED_AHEAD);
+        cp_async_wait<CO_FEED_AHEAD - 1>();
+        f.read(g + 2, a0, a1);
+        ana_group<BANDS>(st, acc, rem, b0, b1, c);
+    }
+    cp_async_wait<0>();
+    if (g < nGroups) {           // odd group count
+        ana_group<BANDS>(st, acc, rem, a0, a1, c);
+        ++g;
     }
     if (!BANDS) // back to the reference's counter for the tail and for the state arrays
         st.cool = max(rem + 1, 0);
-    for (int q = 4 * nGroups; q < n4; ++q) {
-        const float4 v = ld_hint(p + q, keep);
+    if (n & 4) {                 // n % 8 == 4: one last quad
+        const float4 v = ld_hint(reinterpret_cast<const float4*>(f.stream) + 2 * nGroups, f.policy);
         if (BANDS) {
             band_quad(st, acc, v, c);
         } else {
@@ -514,7 +563,6 @@ __device__ __forceinline__ void ana_walk(AnaState& st, AnaAcc& acc, const float*
         }
     }
 }
-#undef JB_LOAD_GROUP
 
 __device__ __forceinline__ StatSums load_stats(const float* s)
 {
@@ -541,7 +589,7 @@ struct CoopArgs {
 
 __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_constant__ CoopArgs ca)
 {
-    extern __shared__ __align__(128) unsigned char smemRaw[];
+    extern __shared__ __align__(1024) unsigned char smemRaw[];
     CoopSmem& sm = *reinterpret_cast<CoopSmem*>(smemRaw);
     const ProcArgs& a = ca.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -551,12 +599,20 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
 
     // roles (uniform over the launch)
     const int nAna = (L * ca.groupClips + 31) / 32;          // envelope-analyzer warps; as many band-analyzer warps
-    const int wEnv = CO_WARPS - nAna, wBand = wEnv - nAna, wScout = wBand - CO_NSCOUT, wBulk = CO_W_BULK;
-    const int nBulk = wScout - wBulk;
-    const bool isProducerWarp = warp == CO_W_PRODUCER;
-    const bool isScoutWarp = warp >= wScout && warp < wBand;
-    const bool isEnvWarp = warp >= wEnv;
-    const bool isBandWarp = warp >= wBand && warp < wEnv;
+    // A warp's scheduler (SM sub-partition) is warp % 4.  The envelope warps carry the kernel's critical
+    // sequential chain and every one of their instructions is on it, so they get sub-partition 3 to
+    // themselves (its other warps idle); everybody else shares sub-partitions 0..2.
+    const bool onSeqPartition = (warp & 3) == 3;
+    const int seqIdx = warp >> 2;                 // index among the warps of sub-partition 3
+    const int parIdx = warp - ((warp + 1) >> 2);  // index among the others
+    const int nPar = CO_WARPS - CO_WARPS / 4;
+    const int wScout = 1, wBand = wScout + CO_NSCOUT, wBulk = wBand + nAna;
+    const int nBulk = nPar - wBulk;
+    const bool isProducerWarp = !onSeqPartition && parIdx == 0;
+    const bool isScoutWarp = !onSeqPartition && parIdx >= wScout && parIdx < wBand;
+    const bool isBandWarp = !onSeqPartition && parIdx >= wBand && parIdx < wBulk;
+    const bool isBulkWarp = !onSeqPartition && parIdx >= wBulk;
+    const bool isEnvWarp = onSeqPartition && seqIdx < nAna;
     const int anaThreads = 2 * nAna * 32;
     const uint64_t polStream = policy_evict_first(), polKeep = policy_evict_last();
 
@@ -593,7 +649,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
         // ---- per-role state for this group
         // scout: Punch envelopes of row (clip, ch)
         float scF = 0.0f, scS = 0.0f;
-        const int scRow = (warp - wScout) * 32 + lane;
+        const int scRow = (parIdx - wScout) * 32 + lane;
         const bool isScout = isScoutWarp && punchFirst && scRow < rows;
         if (isScout) {
             const long long clip = clip0 + (scRow >> 1);
@@ -602,9 +658,12 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             scS = a.state[(long long) (b + PV_SLOW0 + (scRow & 1)) * a.clipPitch + clip];
         }
         // analyzers: lane <-> (plugin slot, clip), once in an envelope warp and once in a band warp
-        const int anaIdx = (warp - (isBandWarp ? wBand : wEnv)) * 32 + lane;
+        const int anaIdx = (isBandWarp ? parIdx - wBand : seqIdx) * 32 + lane;
         const int anaSlot = anaIdx / ca.groupClips, anaClip = anaIdx % ca.groupClips;
         const bool isAna = (isEnvWarp || isBandWarp) && anaSlot < L && anaClip < G;
+        // shared-memory ring row of this analyzer lane, swizzle folded in; pinned to a register
+        uint32_t anaLaneBase = smem_u32(&sm.anaRing[isBandWarp ? 1 : 0][isAna ? anaIdx : 0][0]) ^ ((uint32_t) (lane & 7) << 4);
+        asm volatile("" : "+r"(anaLaneBase));
         AnaState ast {};
         float preScore = 0.0f;
         if (isAna) {
@@ -667,13 +726,17 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             const float* stream = monoCta + ((size_t) anaClip * nSig + sig) * 2 * CO_BLOCKMAX + par * CO_BLOCKMAX;
             if (ca.debugSkip & 16) // probe: every walk re-reads one L1-resident kilobyte per lane
                 stream = monoCta + (size_t) anaIdx * 256;
+            AnaFeed feed;
+            feed.stream = stream;
+            feed.laneBase = anaLaneBase;
+            feed.policy = polKeep;
             if (isAna && !(ca.debugSkip & (isBandWarp ? 2 : 1))) {
                 if (isBandWarp) {
-                    ana_walk<true>(ast, acc, stream, n, ana, polKeep);
+                    ana_walk<true>(ast, acc, feed, n, ana);
                     sm.bandAcc[hand][anaIdx][0] = acc.lowAcc;
                     sm.bandAcc[hand][anaIdx][1] = acc.highAcc;
                 } else {
-                    ana_walk<false>(ast, acc, stream, n, ana, polKeep);
+                    ana_walk<false>(ast, acc, feed, n, ana);
                 }
             }
             named_barrier(CO_BAR_ANA, anaThreads);
@@ -730,13 +793,13 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                     if (single || cur.off == CO_T)
                         analyze_post(cur.blk - 1, a.blockSize);
                 }
-            } else {
+            } else if (isBulkWarp) {
                 // ---- bulk warps
                 mbar_wait(&sm.bar[slot], (step >> 1) & 1);
                 const int nValid = max(0, min(CO_CH, cur.n - lane * CO_CH));
                 const bool firstStep = cur.off == 0;
                 const bool ragged = cur.n < CO_T; // warp-uniform
-                for (int ci = warp - wBulk; ci < G && !(ca.debugSkip & 4); ci += nBulk) {
+                for (int ci = parIdx - wBulk; ci < G && !(ca.debugSkip & 4); ci += nBulk) {
                     float* rowL = &sm.tile[slot][2 * ci][lane * CO_CH];
                     float* rowR = &sm.tile[slot][2 * ci + 1][lane * CO_CH];
                     float l[CO_CH], r[CO_CH];
@@ -843,7 +906,7 @@ const char* jbk_coop_last_error(void) { return g_coopErr; }
 // Scratch the coop kernel needs (mono rings of the analyzer lanes), sized for a full grid.
 size_t jbk_coop_scratch_bytes(int chainLen, int numSMs)
 {
-    return sizeof(float) * (size_t) numSMs * CO_GMAX * (size_t) (chainLen + 1) * 2 * CO_BLOCKMAX;
+    return sizeof(float) * ((size_t) numSMs * CO_GMAX * (size_t) (chainLen + 1) * 2 * CO_BLOCKMAX + CO_FEED_PAD);
 }
 
 // Can this call take the cooperative path?  (Chain made of Punch / Width / Infer with Punch only
