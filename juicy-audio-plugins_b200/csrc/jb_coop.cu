@@ -49,7 +49,13 @@ constexpr int CO_W_PRODUCER = 0;
 constexpr int CO_W_BULK = 1;
 constexpr int CO_NSCOUT = CO_ROWS / 32;                 // 2 warps
 constexpr int CO_ANA_LANES = CO_GMAX * CO_MAXCHAIN;     // 96
-constexpr int CO_WARPS = 20;
+#ifndef JB_CO_WARPS
+#define JB_CO_WARPS 16
+#endif
+#ifndef JB_CO_ISOLATE
+#define JB_CO_ISOLATE 1   // 1: envelope warps alone on SM sub-partition 3; 0: roles by plain warp index
+#endif
+constexpr int CO_WARPS = JB_CO_WARPS;
 constexpr int CO_THREADS = CO_WARPS * 32;               // 672
 constexpr int CO_BAR_ANA = 1;                           // named barrier of the analyzer warps
 
@@ -602,10 +608,17 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
     // A warp's scheduler (SM sub-partition) is warp % 4.  The envelope warps carry the kernel's critical
     // sequential chain and every one of their instructions is on it, so they get sub-partition 3 to
     // themselves (its other warps idle); everybody else shares sub-partitions 0..2.
+#if JB_CO_ISOLATE
     const bool onSeqPartition = (warp & 3) == 3;
     const int seqIdx = warp >> 2;                 // index among the warps of sub-partition 3
     const int parIdx = warp - ((warp + 1) >> 2);  // index among the others
     const int nPar = CO_WARPS - CO_WARPS / 4;
+#else
+    const bool onSeqPartition = warp >= CO_WARPS - nAna;
+    const int seqIdx = warp - (CO_WARPS - nAna);
+    const int parIdx = warp;
+    const int nPar = CO_WARPS - nAna;
+#endif
     const int wScout = 1, wBand = wScout + CO_NSCOUT, wBulk = wBand + nAna;
     const int nBulk = nPar - wBulk;
     const bool isProducerWarp = !onSeqPartition && parIdx == 0;

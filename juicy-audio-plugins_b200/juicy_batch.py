@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjuicy_batch.so")
+LIB_PATH = os.environ.get("JUICY_BATCH_LIB") or os.path.join(HERE, "libjuicy_batch.so")  # override: kernel-variant experiments
 
 JB_OK = 0
 KINDS = ("JuicyInfer", "JuicyPunch", "JuicySaturator", "JuicyWidth", "JuicyCohere", "JuicyTexture", "JuicyMotion")
