@@ -168,7 +168,9 @@ __device__ __forceinline__ float tanh_fast(float x)
     p = fmaf(p, x2, -0x1.55553ep-2f);
     const float small = fmaf(x * x2, p, x);
     const float e = exp2f(ax * 2.885390081777927f); // e^{2|x|}; inf for large |x| -> 1
-    const float big = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+    float rcp;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(e + 1.0f));
+    const float big = copysignf(fmaf(-2.0f, rcp, 1.0f), x);
     return ax < 0.55f ? small : big;
 }
 
@@ -209,23 +211,54 @@ __device__ __forceinline__ void punch_chunk(float (&x)[CO_CH], float2 ck, const 
         const float adry = fabsf(dry);
         fEnv = c.omFast * adry + c.fastCoeff * fEnv;
         sEnv = c.omSlow * adry + c.slowCoeff * sEnv;
+        // from here on pointwise: fused multiply-adds (1e-7 relative, inside the sample tolerance)
         const float transient = jmaxf(0.0f, fEnv - sEnv);
         const float transientCurve = pow_unit(transient, c.curveExp);
-        const float punchGain = 1.0f + c.punchK * transientCurve;
-        const float sustainGain = 1.0f + c.sustainK * jmaxf(0.0f, sEnv - transient * 0.6f);
+        const float punchGain = fmaf(c.punchK, transientCurve, 1.0f);
+        const float sustainGain = fmaf(c.sustainK, jmaxf(0.0f, fmaf(-0.6f, transient, sEnv)), 1.0f);
         float wet = dry * punchGain * sustainGain;
         const float soft = tanh_fast(wet * c.drive) * invTanhDrive;
         const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
-        wet = soft + c.clipAmt * (hard - soft);
-        x[i] = (dry + c.mix * (wet - dry)) * c.outGain;
+        wet = fmaf(c.clipAmt, hard - soft, soft);
+        x[i] = fmaf(c.mix, wet - dry, dry) * c.outGain;
     }
 }
 
 // JuicyWidth/PluginProcessor.cpp:106-137 on one clip's chunk.  width after k in-block multiplies
 // comes from the table (bit-identical to the reference's repeated `width *= dynamicLimit`);
 // the right channel's wet signal goes through the 60 ms ring in global memory (clip-major).
+// The delayed wet-R samples of a step lie in ring positions written by EARLIER steps whenever the
+// delay is at least a step long (and jbk_coop_supported keeps ringLen - delay >= a step, so this
+// step's writes cannot land on them either): then they are fetched at the top of the clip-step
+// and their L2 latency hides behind the stages in front of Width.
+struct WidthPrefetch {
+    float4 v0, v1;
+    bool have;
+};
+__device__ __forceinline__ WidthPrefetch width_prefetch(const WidthCoef& c, const float* ring, int wpos0, int lane, int nValid)
+{
+    WidthPrefetch pf;
+    pf.v0 = pf.v1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    pf.have = c.delaySamples >= CO_T && ((wpos0 | c.ringLen | c.delaySamples) & 3) == 0; // warp-uniform
+    if (pf.have) {
+        int wp = wpos0 + lane * CO_CH;
+        wp -= wp >= c.ringLen ? c.ringLen : 0;
+        int rp0 = wp - c.delaySamples;
+        rp0 += rp0 < 0 ? c.ringLen : 0;
+        int p1 = wp + 4;
+        p1 -= p1 >= c.ringLen ? c.ringLen : 0;
+        int rp1 = p1 - c.delaySamples;
+        rp1 += rp1 < 0 ? c.ringLen : 0;
+        if (nValid > 0)
+            pf.v0 = __ldcg(reinterpret_cast<const float4*>(ring + rp0));
+        if (nValid > 4)
+            pf.v1 = __ldcg(reinterpret_cast<const float4*>(ring + rp1));
+    }
+    return pf;
+}
 __device__ __forceinline__ void width_chunk(float (&l)[CO_CH], float (&r)[CO_CH], const WidthCoef& c, const float* tab,
-                                            int kStart, int& warpTotal, float* ring, int wpos0, int lane, int nValid)
+                                            int kStart, int& warpTotal, float* ring, int wpos0, int lane, int nValid,
+                                            const WidthPrefetch& pf)
 {
     int kk[CO_CH];
     int cnt = 0;
@@ -276,34 +309,39 @@ __device__ __forceinline__ void width_chunk(float (&l)[CO_CH], float (&r)[CO_CH]
                 ring[p] = wetR[i];
         }
     }
-    __syncwarp(); // the delayed read below may land on a value another lane wrote in this step
-    if (vec) {
-#pragma unroll
-        for (int g = 0; g < CO_CH / 4; ++g) {
-            int p = wp + 4 * g;
-            p -= p >= c.ringLen ? c.ringLen : 0;
-            int rp = p - c.delaySamples;
-            rp += rp < 0 ? c.ringLen : 0;
-            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (4 * g < nValid)
-                v = __ldcg(reinterpret_cast<const float4*>(ring + rp));
-            wetR[4 * g] = v.x; wetR[4 * g + 1] = v.y; wetR[4 * g + 2] = v.z; wetR[4 * g + 3] = v.w;
-        }
+    if (pf.have) {
+        wetR[0] = pf.v0.x; wetR[1] = pf.v0.y; wetR[2] = pf.v0.z; wetR[3] = pf.v0.w;
+        wetR[4] = pf.v1.x; wetR[5] = pf.v1.y; wetR[6] = pf.v1.z; wetR[7] = pf.v1.w;
     } else {
+        __syncwarp(); // the delayed read below may land on a value another lane wrote in this step
+        if (vec) {
 #pragma unroll
-        for (int i = 0; i < CO_CH; ++i) {
-            int p = wp + i;
-            p -= p >= c.ringLen ? c.ringLen : 0;
-            int rp = p - c.delaySamples;
-            rp += rp < 0 ? c.ringLen : 0;
-            wetR[i] = (i < nValid) ? __ldcg(ring + rp) : 0.0f;
+            for (int g = 0; g < CO_CH / 4; ++g) {
+                int p = wp + 4 * g;
+                p -= p >= c.ringLen ? c.ringLen : 0;
+                int rp = p - c.delaySamples;
+                rp += rp < 0 ? c.ringLen : 0;
+                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (4 * g < nValid)
+                    v = __ldcg(reinterpret_cast<const float4*>(ring + rp));
+                wetR[4 * g] = v.x; wetR[4 * g + 1] = v.y; wetR[4 * g + 2] = v.z; wetR[4 * g + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CO_CH; ++i) {
+                int p = wp + i;
+                p -= p >= c.ringLen ? c.ringLen : 0;
+                int rp = p - c.delaySamples;
+                rp += rp < 0 ? c.ringLen : 0;
+                wetR[i] = (i < nValid) ? __ldcg(ring + rp) : 0.0f;
+            }
         }
     }
 #pragma unroll
     for (int i = 0; i < CO_CH; ++i) {
         const float dryL = l[i], dryR = r[i];
-        l[i] = (dryL + c.mix * (wetL[i] - dryL)) * c.outGain;
-        r[i] = (dryR + c.mix * (wetR[i] - dryR)) * c.outGain;
+        l[i] = fmaf(c.mix, wetL[i] - dryL, dryL) * c.outGain;
+        r[i] = fmaf(c.mix, wetR[i] - dryR, dryR) * c.outGain;
     }
 }
 
@@ -822,6 +860,11 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                         l[0] = a0.x; l[1] = a0.y; l[2] = a0.z; l[3] = a0.w; l[4] = a1.x; l[5] = a1.y; l[6] = a1.z; l[7] = a1.w;
                         r[0] = b0.x; r[1] = b0.y; r[2] = b0.z; r[3] = b0.w; r[4] = b1.x; r[5] = b1.y; r[6] = b1.z; r[7] = b1.w;
                     }
+                    WidthPrefetch widthPf;
+                    widthPf.have = false;
+                    if (widthSlot >= 0)
+                        widthPf = width_prefetch(a.slot[widthSlot].c.width, a.widthRing + (long long) (clip0 + ci) * a.ringClipStride,
+                                                 sm.widthPos[ci], lane, nValid);
                     if (ragged)
                         mask_chunk(l, r, nValid);
                     float* monoClip = monoCta + ((size_t) ci * nSig) * 2 * CO_BLOCKMAX + blockPar * CO_BLOCKMAX + cur.off + lane * CO_CH;
@@ -838,7 +881,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                             const int wpos0 = sm.widthPos[ci];
                             __syncwarp();
                             float* ring = a.widthRing + (long long) (clip0 + ci) * a.ringClipStride;
-                            width_chunk(l, r, d.c.width, sm.widthTab, kStart, total, ring, wpos0, lane, nValid);
+                            width_chunk(l, r, d.c.width, sm.widthTab, kStart, total, ring, wpos0, lane, nValid, widthPf);
                             if (lane == 0) {
                                 sm.widthCount[ci] = kStart + total;
                                 int np = wpos0 + cur.n;
