@@ -23,6 +23,9 @@ namespace {
 
 using namespace jbdev;
 
+#define JB_CTA_THREADS 32
+#define JB_LANE_CTA_THREADS JB_CTA_THREADS
+
 // Per-sample transcendentals.  The oracle uses glibc's (nearly correctly rounded)
 // float functions; block-rate pow/log10 are evaluated in fp64 and rounded once,
 // Texture-metal's cos restates glibc's own algorithm (below), the others use
@@ -776,6 +779,58 @@ __device__ __forceinline__ void store4(float* p, int i, int n, bool vec, const Q
     }
 }
 
+// ---- sample access (v2): lane-local asynchronous prefetch ring.
+// A lane streams its own two rows, so a warp's loads are 32 separate 16-byte pieces and their L2 /
+// HBM latency (hundreds of cycles) used to sit in front of every four samples.  Each lane now copies
+// its rows with cp.async (no register landing, no scoreboard wait) into a private 2 x 64-sample ring
+// in shared memory 48 samples ahead of use and reads them back one quad ahead.  Piece k of a row is
+// stored at k ^ (lane & 7) so that the 8 lanes of a quarter-warp hit 8 different bank groups.
+constexpr int LF_AHEAD = 12; // quads in flight per row (ring: 16 quads)
+
+__device__ __forceinline__ uint32_t lf_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lf_cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void lf_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void lf_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ Quad lf_lds(uint32_t addr)
+{
+    Quad q;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]) : "r"(addr) : "memory");
+    return q;
+}
+struct LaneFeed {
+    uint32_t base;           // shared address of this lane's 512-byte ring (row L, then row R), swizzle folded in
+    const float *srcL, *srcR;
+    int nQuads;
+    __device__ __forceinline__ void init(const float* l, const float* r, int n)
+    {
+        __shared__ __align__(512) float4 ring[JB_LANE_CTA_THREADS * 32];
+        base = lf_smem_u32(&ring[threadIdx.x * 32]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
+        asm volatile("" : "+r"(base));
+        srcL = l;
+        srcR = r;
+        nQuads = n >> 2;
+    }
+    __device__ __forceinline__ void issue(int q) const // quad q of both rows -> ring piece q & 15; always commits a group
+    {
+        if (q < nQuads) {
+            const uint32_t off = (uint32_t) (q & 15) << 4;
+            lf_cp_async16(base ^ off, srcL + 4 * q);
+            lf_cp_async16((base ^ off) + 256u, srcR + 4 * q);
+        }
+        lf_commit();
+    }
+    __device__ __forceinline__ void read(int q, Quad& l, Quad& r) const
+    {
+        const uint32_t off = (uint32_t) (q & 15) << 4;
+        l = lf_lds(base ^ off);
+        r = lf_lds((base ^ off) + 256u);
+    }
+};
+
 // One sweep over one block of one clip.  mainSlot < 0 for sweep 0.
 template <class Main, class Pre>
 __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
@@ -819,9 +874,7 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
         srcL = dstL;
     }
 
-    for (int i = 0; i < n; i += 4) {
-        Quad ql = load4(srcL, i, n, vec);
-        Quad qr = load4(srcR, i, n, vec);
+    auto quad = [&](Quad& ql, Quad& qr, int i) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (i + k < n) {
@@ -843,6 +896,32 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
             if (!Main::kSeqChannels)
                 store4(dstL, i, n, vec, ql);
             store4(dstR, i, n, vec, qr);
+        }
+    };
+    if (vec) { // every quad is whole (n % 4 == 0): rows come through the lane's prefetch ring
+        LaneFeed feed;
+        feed.init(srcL, srcR, n);
+#pragma unroll
+        for (int q = 0; q < LF_AHEAD; ++q)
+            feed.issue(q);
+        lf_wait<LF_AHEAD - 1>();
+        Quad ql, qr, nl, nr;
+        feed.read(0, ql, qr);
+#pragma unroll 1
+        for (int i = 0, q = 0; i < n; i += 4, ++q) {
+            feed.issue(q + LF_AHEAD);
+            lf_wait<LF_AHEAD - 1>(); // quads <= q + 1 have landed
+            feed.read(q + 1, nl, nr);
+            quad(ql, qr, i);
+            ql = nl;
+            qr = nr;
+        }
+        lf_wait<0>();
+    } else {
+        for (int i = 0; i < n; i += 4) {
+            Quad ql = load4(srcL, i, n, vec);
+            Quad qr = load4(srcR, i, n, vec);
+            quad(ql, qr, i);
         }
     }
 
@@ -904,7 +983,6 @@ __device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, 
     }
 }
 
-#define JB_CTA_THREADS 32
 
 __global__ void __launch_bounds__(JB_CTA_THREADS) jb_process_kernel(const __grid_constant__ ProcArgs a)
 {
