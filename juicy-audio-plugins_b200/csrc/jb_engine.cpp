@@ -292,6 +292,10 @@ int buildArgs(jb_engine* e, ProcArgs& a, const float* dIn, float* dOut, int nSam
     a.chainLen = (int) e->chain.size();
     const bool aligned = ((reinterpret_cast<uintptr_t>(dIn) | reinterpret_cast<uintptr_t>(dOut)) & 15u) == 0;
     a.vecOk = (aligned && nSamples % 4 == 0 && a.rowPitch % 4 == 0 && e->blockSize % 4 == 0) ? 1 : 0;
+    a.octets = nClips >= 32768 ? 1 : 0;
+    for (int k : e->chain)
+        if (k == jb::kPunch || k == jb::kTexture || k == jb::kMotion)
+            a.octets = 0;
     a.ana = jb::makeAnaCoef(e->sampleRate);
     for (size_t s = 0; s < e->chain.size(); ++s) {
         a.slot[s].kind = e->chain[s];
@@ -340,8 +344,17 @@ int launchProcess(jb_engine* e, const ProcArgs& a)
         coop = false;
     else if (e->pathMode == 2 && !coop)
         return fail(JB_ERR_UNSUPPORTED, "cooperative path forced but this chain / call shape is not supported by it");
-    else if (e->pathMode == 0 && coop && a.nClips >= kLaneKernelMinClips)
-        coop = false;
+    else if (e->pathMode == 0 && coop) {
+        // Measured crossover (profiles/README.md): the cooperative kernel renders 32 clips per SM at a time in
+        // ~2.7 ms (one plugin) .. 4.1 ms (Punch -> Width) per second of audio; the lane kernel needs the whole
+        // GPU's worth of lanes.  Analyzer-only chains (Infer) are cheap enough per lane that it wins from ~3 rounds.
+        bool inferOnly = true;
+        for (int k : e->chain)
+            inferOnly = inferOnly && k == jb::kInfer;
+        const int limit = inferOnly ? e->numSMs * 32 * 2 : kLaneKernelMinClips;
+        if (a.nClips > limit)
+            coop = false;
+    }
     JB_CUDA(cudaEventRecord(start, e->stream));
     if (coop) {
         if (jbk_launch_coop(&a, e->dCoopScratch, e->numSMs, e->stream) != 0)

@@ -154,6 +154,7 @@ struct MainBase {
 
 struct MainNone : MainBase { // sweep 0: samples pass through untouched, nothing to publish
     static constexpr bool kHas = false, kSeqChannels = false;
+    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     __device__ __forceinline__ void load(const Lane&, const SlotDesc&, int) {}
     __device__ __forceinline__ void step(float&, float&) {}
     __device__ __forceinline__ void store(const Lane&, const SlotDesc&) {}
@@ -162,6 +163,7 @@ struct MainNone : MainBase { // sweep 0: samples pass through untouched, nothing
 // JuicyInfer/PluginProcessor.cpp:78-81: buffer.applyGain(trimGain) between the two analyses
 struct MainInfer : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
+    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     float g;
     int mode;
     __device__ __forceinline__ void load(const Lane&, const SlotDesc& d, int)
@@ -186,6 +188,7 @@ struct MainInfer : MainBase {
 // JuicySaturator/PluginProcessor.cpp:83-98
 struct MainSat : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
+    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     float s0, s1;
     SatCoef c;
     __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
@@ -220,6 +223,7 @@ struct MainSat : MainBase {
 // JuicyPunch/PluginProcessor.cpp:86-112
 struct MainPunch : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
+    static constexpr bool kHeavy = true; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     float f0, f1, sl0, sl1;
     PunchCoef c;
     __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
@@ -266,6 +270,7 @@ struct MainPunch : MainBase {
 // time-major ring [ringLen][clip], so a warp's accesses coalesce.
 struct MainWidth : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
+    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     float width;
     int wpos;
     WidthCoef c;
@@ -305,6 +310,7 @@ struct MainWidth : MainBase {
 // JuicyCohere/PluginProcessor.cpp:99-119 (lpA/lpB restart at 0 every block, :103-104)
 struct MainCohere : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
+    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     float t0, t1, a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
     float lowComp, midComp, highComp;
     CohereCoef c;
@@ -383,6 +389,7 @@ struct TexChan {
 template <int MAT>
 struct MainTexture : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
+    static constexpr bool kHeavy = true; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     TexChan ch0, ch1;
     uint32_t rng0, rng1;
     int waveIdx;
@@ -570,6 +577,7 @@ struct MainTexture : MainBase {
 // the main part runs as two sequential channel passes (kSeqChannels).
 struct MainMotion : MainBase {
     static constexpr bool kHas = true, kSeqChannels = true;
+    static constexpr bool kHeavy = true; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     float vTone, vTrans, vTail, tTone, tTrans, tTail, phase, budget;
     float tail0, tail1, lp0, lp1, prev0, prev1, repScale, recovery;
     MotionCoef c;
@@ -782,15 +790,21 @@ __device__ __forceinline__ void store4(float* p, int i, int n, bool vec, const Q
 // ---- sample access (v2): lane-local asynchronous prefetch ring.
 // A lane streams its own two rows, so a warp's loads are 32 separate 16-byte pieces and their L2 /
 // HBM latency (hundreds of cycles) used to sit in front of every four samples.  Each lane now copies
-// its rows with cp.async (no register landing, no scoreboard wait) into a private 2 x 64-sample ring
-// in shared memory 48 samples ahead of use and reads them back one quad ahead.  Piece k of a row is
+// its rows with cp.async (no register landing, no scoreboard wait) into a private 2 x 32-sample ring
+// in shared memory 24 samples ahead of use and reads them back one quad ahead.  Piece k of a row is
 // stored at k ^ (lane & 7) so that the 8 lanes of a quarter-warp hit 8 different bank groups.
-constexpr int LF_AHEAD = 12; // quads in flight per row (ring: 16 quads)
+constexpr int LF_AHEAD = 6; // quads in flight per row (ring: 8 quads = 128 B per row, 8 KB per warp: 16+ warps per SM stay resident)
 
 __device__ __forceinline__ uint32_t lf_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+// CACHE_L1: the 32-byte sector a piece belongs to is kept in L1, so the row's next piece does not go to L2 again
+// (big light batches, where L2 sector throughput is the bound); otherwise the copies bypass L1.
+template <bool CACHE_L1>
 __device__ __forceinline__ void lf_cp_async16(uint32_t dst, const void* src)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    if (CACHE_L1)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void lf_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -802,34 +816,43 @@ __device__ __forceinline__ Quad lf_lds(uint32_t addr)
     return q;
 }
 struct LaneFeed {
-    uint32_t base;           // shared address of this lane's 512-byte ring (row L, then row R), swizzle folded in
+    uint32_t base;           // shared address of this lane's 256-byte ring (row L, then row R), swizzle folded in
     const float *srcL, *srcR;
     int nQuads;
     __device__ __forceinline__ void init(const float* l, const float* r, int n)
     {
-        __shared__ __align__(512) float4 ring[JB_LANE_CTA_THREADS * 32];
-        base = lf_smem_u32(&ring[threadIdx.x * 32]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
+        __shared__ __align__(256) float4 ring[JB_LANE_CTA_THREADS * 16];
+        base = lf_smem_u32(&ring[threadIdx.x * 16]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
         asm volatile("" : "+r"(base));
         srcL = l;
         srcR = r;
         nQuads = n >> 2;
     }
-    __device__ __forceinline__ void issue(int q) const // quad q of both rows -> ring piece q & 15; always commits a group
+    template <bool CACHE_L1>
+    __device__ __forceinline__ void issue(int q) const // quad q of both rows -> ring piece q & 7; always commits a group
     {
         if (q < nQuads) {
-            const uint32_t off = (uint32_t) (q & 15) << 4;
-            lf_cp_async16(base ^ off, srcL + 4 * q);
-            lf_cp_async16((base ^ off) + 256u, srcR + 4 * q);
+            const uint32_t off = (uint32_t) (q & 7) << 4;
+            lf_cp_async16<CACHE_L1>(base ^ off, srcL + 4 * q);
+            lf_cp_async16<CACHE_L1>((base ^ off) + 128u, srcR + 4 * q);
         }
         lf_commit();
     }
     __device__ __forceinline__ void read(int q, Quad& l, Quad& r) const
     {
-        const uint32_t off = (uint32_t) (q & 15) << 4;
+        const uint32_t off = (uint32_t) (q & 7) << 4;
         l = lf_lds(base ^ off);
-        r = lf_lds((base ^ off) + 256u);
+        r = lf_lds((base ^ off) + 128u);
     }
 };
+
+// Eight samples = one 32-byte sector per store (STG.256, sm_100): half the L2 write requests of two 16-byte stores.
+__device__ __forceinline__ void store8(float* p, const Quad& a, const Quad& b)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.v[0]), "f"(a.v[1]), "f"(a.v[2]), "f"(a.v[3]),
+                 "f"(b.v[0]), "f"(b.v[1]), "f"(b.v[2]), "f"(b.v[3])
+                 : "memory");
+}
 
 // One sweep over one block of one clip.  mainSlot < 0 for sweep 0.
 template <class Main, class Pre>
@@ -874,7 +897,7 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
         srcL = dstL;
     }
 
-    auto quad = [&](Quad& ql, Quad& qr, int i) {
+    auto quad_math = [&](Quad& ql, Quad& qr, int i) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (i + k < n) {
@@ -892,6 +915,9 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
                 qr.v[k] = r;
             }
         }
+    };
+    auto quad = [&](Quad& ql, Quad& qr, int i) {
+        quad_math(ql, qr, i);
         if (mustWrite) {
             if (!Main::kSeqChannels)
                 store4(dstL, i, n, vec, ql);
@@ -901,22 +927,62 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
     if (vec) { // every quad is whole (n % 4 == 0): rows come through the lane's prefetch ring
         LaneFeed feed;
         feed.init(srcL, srcR, n);
+        if (Main::kHeavy || !a.octets) {
 #pragma unroll
-        for (int q = 0; q < LF_AHEAD; ++q)
-            feed.issue(q);
-        lf_wait<LF_AHEAD - 1>();
-        Quad ql, qr, nl, nr;
-        feed.read(0, ql, qr);
+            for (int q = 0; q < LF_AHEAD; ++q)
+                feed.issue<false>(q);
+            lf_wait<LF_AHEAD - 1>();
+            Quad ql, qr, nl, nr;
+            feed.read(0, ql, qr);
 #pragma unroll 1
-        for (int i = 0, q = 0; i < n; i += 4, ++q) {
-            feed.issue(q + LF_AHEAD);
-            lf_wait<LF_AHEAD - 1>(); // quads <= q + 1 have landed
-            feed.read(q + 1, nl, nr);
-            quad(ql, qr, i);
-            ql = nl;
-            qr = nr;
+            for (int i = 0, q = 0; i < n; i += 4, ++q) {
+                feed.issue<false>(q + LF_AHEAD);
+                lf_wait<LF_AHEAD - 1>(); // quads <= q + 1 have landed
+                feed.read(q + 1, nl, nr);
+                quad(ql, qr, i);
+                ql = nl;
+                qr = nr;
+            }
+            lf_wait<0>();
+        } else {
+#pragma unroll
+            for (int q = 0; q < LF_AHEAD; ++q)
+                feed.issue<true>(q);
+            const bool wide = ((reinterpret_cast<uintptr_t>(dstL) | reinterpret_cast<uintptr_t>(dstR)) & 31u) == 0;
+            const int nOct = n >> 3;
+            int q = 0;
+#pragma unroll 1
+            for (int o = 0; o < nOct; ++o, q += 2) {
+                Quad l0, r0, l1, r1;
+                feed.issue<true>(q + LF_AHEAD);
+                feed.issue<true>(q + LF_AHEAD + 1);
+                lf_wait<LF_AHEAD>();     // quads <= q + 1 have landed
+                feed.read(q, l0, r0);
+                feed.read(q + 1, l1, r1);
+                quad_math(l0, r0, 4 * q);
+                quad_math(l1, r1, 4 * q + 4);
+                if (mustWrite) {
+                    if (wide) {
+                        if (!Main::kSeqChannels)
+                            store8(dstL + 4 * q, l0, l1);
+                        store8(dstR + 4 * q, r0, r1);
+                    } else {
+                        if (!Main::kSeqChannels) {
+                            store4(dstL, 4 * q, n, vec, l0);
+                            store4(dstL, 4 * q + 4, n, vec, l1);
+                        }
+                        store4(dstR, 4 * q, n, vec, r0);
+                        store4(dstR, 4 * q + 4, n, vec, r1);
+                    }
+                }
+            }
+            lf_wait<0>();
+            if (n & 4) { // one last quad
+                Quad ql, qr;
+                feed.read(q, ql, qr);
+                quad(ql, qr, 4 * q);
+            }
         }
-        lf_wait<0>();
     } else {
         for (int i = 0; i < n; i += 4) {
             Quad ql = load4(srcL, i, n, vec);
@@ -984,7 +1050,7 @@ __device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, 
 }
 
 
-__global__ void __launch_bounds__(JB_CTA_THREADS) jb_process_kernel(const __grid_constant__ ProcArgs a)
+__global__ void __launch_bounds__(JB_CTA_THREADS, 16) jb_process_kernel(const __grid_constant__ ProcArgs a)
 {
     const long long clip = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (clip >= a.nClips)

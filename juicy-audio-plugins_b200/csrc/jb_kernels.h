@@ -152,6 +152,8 @@ struct ProcArgs {
     int histFirstBlock, histMaxBlocks;
     int chainLen;
     int vecOk;             // 16-byte vector path legal (alignment + sizes)
+    int octets;            // lane kernel: 8 samples per trip + 32-byte stores (set for big batches of light chains, where
+                           // L2 sector throughput is the bound; costs registers, so not for Punch / Texture / Motion chains)
     AnaCoef ana;
     SlotDesc slot[JBK_MAX_CHAIN];
 };
