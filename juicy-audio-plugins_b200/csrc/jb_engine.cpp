@@ -348,10 +348,13 @@ int launchProcess(jb_engine* e, const ProcArgs& a)
         // Measured crossover (profiles/README.md): the cooperative kernel renders 32 clips per SM at a time in
         // ~2.7 ms (one plugin) .. 4.1 ms (Punch -> Width) per second of audio; the lane kernel needs the whole
         // GPU's worth of lanes.  Analyzer-only chains (Infer) are cheap enough per lane that it wins from ~3 rounds.
-        bool inferOnly = true;
-        for (int k : e->chain)
+        bool inferOnly = true, hasPunch = false;
+        for (int k : e->chain) {
             inferOnly = inferOnly && k == jb::kInfer;
-        const int limit = inferOnly ? e->numSMs * 32 * 2 : kLaneKernelMinClips;
+            hasPunch = hasPunch || k == jb::kPunch;
+        }
+        // rounds of 32 clips per SM up to which the cooperative kernel stays ahead (Infer 2, Width chains 6, Punch chains 16)
+        const int limit = e->numSMs * 32 * (inferOnly ? 2 : (hasPunch ? 16 : 6));
         if (a.nClips > limit)
             coop = false;
     }
@@ -482,7 +485,7 @@ int jb_prepare(jb_engine* e, double sample_rate, int samples_per_block)
         if (!((k == jb::kPunch && i == 0) || k == jb::kWidth || k == jb::kInfer))
             e->coopCapable = false;
     }
-    e->ringClipMajor = e->coopCapable;
+    e->ringClipMajor = true; // both kernels: each clip owns a contiguous ring (16-byte quads)
     if (e->numSMs == 0) {
         JB_CUDA(cudaDeviceGetAttribute(&e->numSMs, cudaDevAttrMultiProcessorCount, e->device));
     }

@@ -148,6 +148,8 @@ struct AnaWalk {
 // must precede channel 1's), load/store of per-clip state, step(l, r) in place.
 
 struct MainBase {
+    __device__ __forceinline__ void quad_begin() {} // around every group of four whole samples (vector path only)
+    __device__ __forceinline__ void quad_end() {}
     __device__ __forceinline__ float stepCh0(float l) { return l; }
     __device__ __forceinline__ bool writes(bool outOfPlace) const { return true; }
 };
@@ -266,8 +268,13 @@ struct MainPunch : MainBase {
 };
 
 // JuicyWidth/PluginProcessor.cpp:91-137.  The delay line keeps only the right
-// channel's wet signal (the left ring is written but never read, :122,:131) in a
-// time-major ring [ringLen][clip], so a warp's accesses coalesce.
+// channel's wet signal (the left ring is written but never read, :122,:131).
+// Ring layouts: clip-major [clip][ringLen] (pitch 1; what the engine uses) or time-major
+// [ringLen][clip].  With the clip-major ring and everything a multiple of four samples (ring
+// length, delay, write position: the usual 2880 / 576 case) a quad of wet samples is stored with
+// one 16-byte store and the delayed quad is fetched with one 16-byte load issued a quad EARLY --
+// the delayed samples were written delaySamples ago -- so the ring's L2 / HBM latency no longer
+// sits in front of every sample (it was 55 % of all stall samples, profiles/r01_width_lane_*).
 struct MainWidth : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
     static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
@@ -276,6 +283,19 @@ struct MainWidth : MainBase {
     WidthCoef c;
     float* ring;
     long long pitch;
+    bool quads;          // vector ring path
+    static constexpr int kDepth = 1; // quads fetched ahead of use (needs delay >= 4 * kDepth + 4)
+    float4 ahead[kDepth]; // delayed quads of the next kDepth quad_begin calls
+    float d0, d1, d2, d3; // delayed samples of the current quad, next first
+    float w0, w1, w2, w3; // wet samples of the current quad, oldest first (static shifts keep both in registers)
+    __device__ __forceinline__ int delayed_pos(int p) const
+    {
+        int rp = p - c.delaySamples;
+        if (rp < 0)
+            rp += c.ringLen;
+        return rp;
+    }
+    __device__ __forceinline__ int wrap(int p) const { return p >= c.ringLen ? p - c.ringLen : p; }
     __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
     {
         c = d.c.width;
@@ -283,6 +303,34 @@ struct MainWidth : MainBase {
         wpos = L.ldi(d.stateBase + AV_COUNT + WV_WPOS);
         ring = L.a.widthRing + L.clip * L.a.ringClipStride;
         pitch = L.a.ringTimeStride;
+        quads = L.a.vecOk != 0 && pitch == 1 && ((c.ringLen | c.delaySamples | wpos | (int) L.a.ringClipStride) & 3) == 0
+                && c.delaySamples >= 4 * kDepth + 4 && c.ringLen >= 8 * kDepth + 8;
+        d0 = d1 = d2 = d3 = w0 = w1 = w2 = w3 = 0.0f;
+        if (quads) {
+#pragma unroll
+            for (int j = 0; j < kDepth; ++j)
+                ahead[j] = *reinterpret_cast<const float4*>(ring + delayed_pos(wrap(wpos + 4 * j)));
+        }
+    }
+    __device__ __forceinline__ void quad_begin()
+    {
+        if (!quads)
+            return;
+        d0 = ahead[0].x; d1 = ahead[0].y; d2 = ahead[0].z; d3 = ahead[0].w;
+#pragma unroll
+        for (int j = 0; j + 1 < kDepth; ++j)
+            ahead[j] = ahead[j + 1];
+        // the quad used kDepth calls from now was written >= 4 samples ago (delay >= 4 kDepth + 4)
+        ahead[kDepth - 1] = *reinterpret_cast<const float4*>(ring + delayed_pos(wrap(wpos + 4 * kDepth)));
+    }
+    __device__ __forceinline__ void quad_end()
+    {
+        if (!quads)
+            return;
+        *reinterpret_cast<float4*>(ring + wpos) = make_float4(w0, w1, w2, w3);
+        wpos += 4;
+        if (wpos >= c.ringLen)
+            wpos = 0;
     }
     __device__ __forceinline__ void step(float& l, float& r)
     {
@@ -294,15 +342,18 @@ struct MainWidth : MainBase {
         const float side = 0.5f * (dryL - dryR) * (1.0f + width);
         const float wetL = mid + side;
         float wetR = mid - side;
-        ring[(long long) wpos * pitch] = wetR;
-        int readPos = wpos - c.delaySamples;
-        if (readPos < 0)
-            readPos += c.ringLen;
-        wetR = ring[(long long) readPos * pitch];
+        if (quads) {
+            w0 = w1; w1 = w2; w2 = w3; w3 = wetR;
+            wetR = d0;
+            d0 = d1; d1 = d2; d2 = d3;
+        } else {
+            ring[(long long) wpos * pitch] = wetR;
+            wetR = ring[(long long) delayed_pos(wpos) * pitch];
+            if (++wpos >= c.ringLen)
+                wpos = 0;
+        }
         l = (dryL + c.mix * (wetL - dryL)) * c.outGain;
         r = (dryR + c.mix * (wetR - dryR)) * c.outGain;
-        if (++wpos >= c.ringLen)
-            wpos = 0;
     }
     __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d) { L.sti(d.stateBase + AV_COUNT + WV_WPOS, wpos); }
 };
@@ -898,6 +949,8 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
     }
 
     auto quad_math = [&](Quad& ql, Quad& qr, int i) {
+        if (vec)
+            mainPart.quad_begin();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (i + k < n) {
@@ -915,6 +968,8 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
                 qr.v[k] = r;
             }
         }
+        if (vec)
+            mainPart.quad_end();
     };
     auto quad = [&](Quad& ql, Quad& qr, int i) {
         quad_math(ql, qr, i);
