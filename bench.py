@@ -304,6 +304,8 @@ def run_engine_arm(args):
         ms_total = e0.elapsed_time(e1)
         kernel_ms, kernel_launches = eng.kernel_time_ms()
         launches = jb.launch_count() - launches0
+        coop_launches, lane_launches = eng.path_launches()
+        kernel_name = "jb_coop_kernel" if coop_launches >= lane_launches else "jb_process_kernel"
 
         # ---- end to end through the C ABI with pinned host buffers
         h_in = jb.PinnedBuffer((n_clips, 2, n))
@@ -347,7 +349,8 @@ def run_engine_arm(args):
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("bytes_per_launch") if tj.get("kernel") == kernel_name else None
         except Exception:
             traffic = None
 
@@ -357,7 +360,7 @@ def run_engine_arm(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "jb_process_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_launch": alg_bytes,
                          "mean_launch_ms": mean_launch_ms, "launches_timed": kernel_launches, "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": count * 4,

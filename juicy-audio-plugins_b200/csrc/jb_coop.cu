@@ -148,32 +148,6 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---------------------------------------------------------------- pointwise math of the bulk lanes
-// std::pow(t, e) for t >= 0, 0 < e < 1 (JuicyPunch/PluginProcessor.cpp:100): 2^(e * log2 t) on the
-// MUFU unit.  |rel err| <~ 3e-6 at the smallest t that still matters.
-__device__ __forceinline__ float pow_unit(float t, float e)
-{
-    const float r = exp2f(e * __log2f(t)); // log2(0) = -inf -> 2^-inf = 0
-    return r;
-}
-// std::tanh: odd minimax polynomial below 0.55 (rel err 8e-8), 1 - 2/(e^{2|x|} + 1) above.
-__device__ __forceinline__ float tanh_fast(float x)
-{
-    const float ax = fabsf(x);
-    const float x2 = x * x;
-    float p = -0x1.825866p-8f;
-    p = fmaf(p, x2, 0x1.54b8a4p-6f);
-    p = fmaf(p, x2, -0x1.b898dep-5f);
-    p = fmaf(p, x2, 0x1.1109aep-3f);
-    p = fmaf(p, x2, -0x1.55553ep-2f);
-    const float small = fmaf(x * x2, p, x);
-    const float e = exp2f(ax * 2.885390081777927f); // e^{2|x|}; inf for large |x| -> 1
-    float rcp;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(e + 1.0f));
-    const float big = copysignf(fmaf(-2.0f, rcp, 1.0f), x);
-    return ax < 0.55f ? small : big;
-}
-
 // ---------------------------------------------------------------- time cursor over the call's steps
 struct Cursor {
     int blk, off, pos, n, nBlk; // host block, offset inside it, absolute sample, step length, block length

@@ -353,8 +353,10 @@ int launchProcess(jb_engine* e, const ProcArgs& a)
             inferOnly = inferOnly && k == jb::kInfer;
             hasPunch = hasPunch || k == jb::kPunch;
         }
-        // rounds of 32 clips per SM up to which the cooperative kernel stays ahead (Infer 2, Width chains 6, Punch chains 16)
-        const int limit = e->numSMs * 32 * (inferOnly ? 2 : (hasPunch ? 16 : 6));
+        // rounds of 32 clips per SM up to which the cooperative kernel stays ahead (profiles/r01_survey_cross.txt):
+        // Infer alone 2, Punch alone 3, Width (+Infer) 6, Punch -> Width 7
+        const int rounds = inferOnly ? 2 : (hasPunch ? (e->chain.size() == 1 ? 3 : 7) : 6);
+        const int limit = e->numSMs * 32 * rounds;
         if (a.nClips > limit)
             coop = false;
     }

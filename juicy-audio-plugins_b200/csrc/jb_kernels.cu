@@ -204,7 +204,7 @@ struct MainSat : MainBase {
     {
         const float driven = dry * c.inGain;
         const float skewed = driven + c.asym * driven * driven;
-        const float soft = tanhf(skewed);
+        const float soft = tanh_fast(skewed); // MUFU-based, <= 1e-7 absolute (jb_device.cuh)
         state += c.toneCoeff * (soft - state);
         const float wet = state * c.outGain;
         return dry + c.mix * (wet - dry);
@@ -226,11 +226,12 @@ struct MainSat : MainBase {
 struct MainPunch : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
     static constexpr bool kHeavy = true; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
-    float f0, f1, sl0, sl1;
+    float f0, f1, sl0, sl1, invTanhDrive;
     PunchCoef c;
     __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
     {
         c = d.c.punch;
+        invTanhDrive = 1.0f / c.tanhDrive;
         const int b = d.stateBase + AV_COUNT;
         f0 = L.ld(b + PV_FAST0);
         f1 = L.ld(b + PV_FAST1);
@@ -243,11 +244,11 @@ struct MainPunch : MainBase {
         fEnv = c.omFast * adry + c.fastCoeff * fEnv;
         sEnv = c.omSlow * adry + c.slowCoeff * sEnv;
         const float transient = jmaxf(0.0f, fEnv - sEnv);
-        const float transientCurve = powf(transient, c.curveExp);
+        const float transientCurve = pow_unit(transient, c.curveExp); // MUFU-based (jb_device.cuh), like the cooperative kernel
         const float punchGain = 1.0f + c.punchK * transientCurve;
         const float sustainGain = 1.0f + c.sustainK * jmaxf(0.0f, sEnv - transient * 0.6f);
         float wet = dry * punchGain * sustainGain;
-        const float soft = tanhf(wet * c.drive) / c.tanhDrive;
+        const float soft = tanh_fast(wet * c.drive) * invTanhDrive;
         const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
         wet = soft + c.clipAmt * (hard - soft);
         return (dry + c.mix * (wet - dry)) * c.outGain;
