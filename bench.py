@@ -71,6 +71,25 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU before any pinned host memory is allocated, so
+    the staging buffers of jb_process_host sit on the GPU's own NUMA node (matters once several ranks share a host)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return allowed
+    except Exception:
+        return None  # plumbing only: without NVML the rank simply stays where the launcher put it
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -243,6 +262,7 @@ def run_engine_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    all_cpus = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -371,6 +391,8 @@ def run_engine_arm(args):
             "mean_juiciness": float(np.mean(rec_host[:, 13])) if rec_host is not None else None,
         }
         if world == 1 and not args.no_cpu:
+            if all_cpus:
+                os.sched_setaffinity(0, all_cpus)  # the CPU leg uses every host core again
             threads = host_threads()
             cpu_clips = args.cpu_clips or max(threads * 32, 64)
             kind, used, secs = cpu_reference_run(cpu_clips, n, threads, 1, 2)
