@@ -290,6 +290,8 @@ int buildArgs(jb_engine* e, ProcArgs& a, const float* dIn, float* dOut, int nSam
     a.histFirstBlock = (int) std::min<long long>(e->blocksDone, 0x7fffffff);
     a.histMaxBlocks = e->histMaxBlocks;
     a.chainLen = (int) e->chain.size();
+    a.recSlotBase = 0;
+    a.recChainLen = a.chainLen;
     const bool aligned = ((reinterpret_cast<uintptr_t>(dIn) | reinterpret_cast<uintptr_t>(dOut)) & 15u) == 0;
     a.vecOk = (aligned && nSamples % 4 == 0 && a.rowPitch % 4 == 0 && e->blockSize % 4 == 0) ? 1 : 0;
     a.octets = nClips >= 32768 ? 1 : 0;
@@ -366,8 +368,31 @@ int launchProcess(jb_engine* e, const ProcArgs& a)
             return fail(JB_ERR_CUDA, "%s", jbk_coop_last_error());
         ++e->coopLaunches;
     } else {
-        if (jbk_launch_process(&a, e->stream) != 0)
+        // Lane kernel, chain of several plugins: one launch per plugin over the whole call (plugin s + 1 only
+        // needs plugin s's output of the same block, and every plugin blocks identically, so plugin-by-plugin
+        // equals block-by-block).  A single-plugin launch is small code with no spills and picks its own
+        // 8-samples-per-trip mode; the fused 8-sweep kernel took 2.5x the sum of its parts.
+        // Measured (profiles/r01_survey_chain.txt): 7-plugin chain on 32768 clips 424 -> 161 ms; below ~20k clips
+        // the render is latency-bound and the two modes tie.  JB_LANE_SPLIT=0/1 forces a mode.
+        const char* splitEnv = std::getenv("JB_LANE_SPLIT");
+        const int splitMode = splitEnv == nullptr ? -1 : std::atoi(splitEnv);
+        const bool splitChains = splitMode < 0 ? a.nClips >= 20480 : splitMode != 0;
+        const int L = a.chainLen;
+        if (L > 1 && splitChains) {
+            for (int s = 0; s < L; ++s) {
+                ProcArgs one = a;
+                one.in = s == 0 ? a.in : a.out;
+                one.chainLen = 1;
+                one.slot[0] = a.slot[s];
+                one.recSlotBase = s;
+                one.recChainLen = L;
+                one.octets = a.nClips >= 32768 && !(one.slot[0].kind == jb::kPunch || one.slot[0].kind == jb::kTexture || one.slot[0].kind == jb::kMotion);
+                if (jbk_launch_process(&one, e->stream) != 0)
+                    return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
+            }
+        } else if (jbk_launch_process(&a, e->stream) != 0) {
             return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
+        }
         ++e->laneLaunches;
     }
     JB_CUDA(cudaEventRecord(stop, e->stream));

@@ -151,6 +151,8 @@ struct ProcArgs {
     int nClips, nCh, nSamples, blockSize;
     int histFirstBlock, histMaxBlocks;
     int chainLen;
+    int recSlotBase, recChainLen; // a launch may render one plugin of a longer chain: its records go to slot recSlotBase + s
+                                  // of a record block laid out for recChainLen plugins
     int vecOk;             // 16-byte vector path legal (alignment + sizes)
     int octets;            // lane kernel: 8 samples per trip + 32-byte stores (set for big batches of light chains, where
                            // L2 sector throughput is the bound; costs registers, so not for Punch / Texture / Motion chains)

@@ -298,3 +298,27 @@ def test_host_streaming_slices_and_passes_are_exact(jb, monkeypatch):
     assert np.array_equal(whole, sliced)
     for a, b in zip(hist_whole, hist_sliced):
         assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_lane_kernel_split_chain_equals_fused_chain(jb, monkeypatch):
+    """Big lane-kernel batches render a chain as one launch per plugin (plugin-by-plugin == block-by-block for
+    causal plugins with identical blocking); both modes must give the same bits."""
+    n_clips, n = 64, 5 * BLOCK + 100
+    clips = jb.synth_clips("mixed", 11, n_clips, n)
+
+    def render(mode):
+        monkeypatch.setenv("JB_LANE_SPLIT", mode)
+        eng = jb.BatchProcessor(FULL_CHAIN, n_clips)
+        eng.set_path("lane")
+        eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+        eng.enableHistory(8)
+        out = eng.processBlock(clips)
+        hist = [eng.getHistory(s) for s in range(len(FULL_CHAIN))]
+        eng.close()
+        return out, hist
+
+    fused, hist_fused = render("0")
+    split, hist_split = render("1")
+    assert np.array_equal(fused, split)
+    for a, b in zip(hist_fused, hist_split):
+        assert np.array_equal(a, b)
