@@ -148,6 +148,22 @@ int jb_enable_history(jb_engine* e, int max_blocks);
 int jb_history_blocks(const jb_engine* e);
 int jb_get_history(jb_engine* e, int slot, int first_block, int n_blocks, jb_metrics* out);
 
+/* Meter-panel statistics of a render: what the plugin editor's JuicyMeterPanel of every clip would
+ * hold after being handed the records of blocks first_block, first_block + block_stride, ... of the
+ * history in order (JuicyMeterPanel::setMetrics / smoothValue / updateStats,
+ * src/shared/JuicyMeterPanel.cpp:3-34,54-71; the editor calls it from a 20 Hz timer with
+ * getLatestMetrics(), src/shared/JuicyPluginEditor.cpp:36,85-89 -- block_stride 1 feeds every block).
+ * Reduced on the device from the history (jb_enable_history first).  out: n_clips records. */
+typedef struct jb_meter_stat { float min, max, avg; } jb_meter_stat;
+typedef struct jb_meter_stats {
+    float preScore, postScore, score, punch, richness, clarity, width, monoSafety; /* smoothed bar values */
+    jb_meter_stat punchStats, richnessStats, clarityStats, widthStats, monoSafetyStats;
+    jb_meter_stat emphasisStats, coherenceStats, synesthesiaStats, fatigueStats, repetitionStats;
+    float count;    /* records fed (MetricStats::count) */
+    float reserved;
+} jb_meter_stats;
+int jb_meter_statistics(jb_engine* e, int slot, int first_block, int n_blocks, int block_stride, jb_meter_stats* out);
+
 /* Seeded synthetic clips written straight into device memory:
  * kind 0 sweep, 1 noise, 2 impulse train, 3 drum hit, 4 mixed (clip mod 4).
  * first_clip offsets the per-clip seeds so shards of one job stay distinct. */

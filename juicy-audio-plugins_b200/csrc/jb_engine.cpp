@@ -859,6 +859,43 @@ int jb_get_history(jb_engine* e, int slot, int first_block, int n_blocks, jb_met
     return JB_OK;
 }
 
+int jb_meter_statistics(jb_engine* e, int slot, int first_block, int n_blocks, int block_stride, jb_meter_stats* out)
+{
+    static_assert(sizeof(jb_meter_stats) == sizeof(float) * JBK_METER, "jb_meter_stats is 40 floats");
+    if (int rc = checkSlot(e, slot))
+        return rc;
+    if (int rc = setDevice(e))
+        return rc;
+    if (e->dHist == nullptr)
+        return fail(JB_ERR_STATE, "jb_meter_statistics: history not enabled");
+    if (out == nullptr || first_block < 0 || n_blocks < 0 || block_stride < 1 || first_block + n_blocks > jb_history_blocks(e))
+        return fail(JB_ERR_ARG, "jb_meter_statistics: block range [%d, %d) stride %d outside the %d recorded blocks", first_block,
+                    first_block + n_blocks, block_stride, jb_history_blocks(e));
+    float* dOut = nullptr;
+    const size_t count = (size_t) JBK_METER * (size_t) e->clipPitch;
+    JB_CUDA(cudaMalloc(&dOut, sizeof(float) * count));
+    int rc = JB_OK;
+    if (jbk_launch_meter(e->dHist, e->clipPitch, (int) e->chain.size(), slot, first_block, n_blocks, block_stride, e->nClips, dOut,
+                         e->stream) != 0)
+        rc = fail(JB_ERR_CUDA, "jb_meter_statistics: kernel launch failed");
+    if (rc == JB_OK) {
+        e->hostScratch.resize(count);
+        cudaError_t err = cudaMemcpyAsync(e->hostScratch.data(), dOut, sizeof(float) * count, cudaMemcpyDeviceToHost, e->stream);
+        if (err == cudaSuccess)
+            err = cudaStreamSynchronize(e->stream);
+        if (err != cudaSuccess)
+            rc = fail(JB_ERR_CUDA, "jb_meter_statistics: %s", cudaGetErrorString(err));
+    }
+    cudaFree(dOut);
+    if (rc != JB_OK)
+        return rc;
+    float* o = reinterpret_cast<float*>(out);
+    for (int c = 0; c < e->nClips; ++c)
+        for (int f = 0; f < JBK_METER; ++f)
+            o[(size_t) c * JBK_METER + f] = e->hostScratch[(size_t) f * (size_t) e->clipPitch + c];
+    return JB_OK;
+}
+
 int jb_set_path(jb_engine* e, int mode)
 {
     if (int rc = checkEngine(e))

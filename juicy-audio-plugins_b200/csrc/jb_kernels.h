@@ -171,6 +171,10 @@ int jbk_launch_synth(float* dAudio, int kind, long long firstClip, int nClips, i
 const char* jbk_last_cuda_error(void);
 long long jbk_launch_count(void);
 void jbk_note_launch(void);
+// jb_meter.cu
+#define JBK_METER 40
+int jbk_launch_meter(const float* hist, long long clipPitch, int chainLen, int slot, int firstBlock, int nBlocks,
+                     int stride, int nClips, float* out, void* stream);
 // jb_coop.cu
 int jbk_coop_supported(const ProcArgs* args);
 size_t jbk_coop_scratch_bytes(int chainLen, int numSMs);

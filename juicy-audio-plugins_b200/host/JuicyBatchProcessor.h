@@ -116,6 +116,13 @@ public:
             check(jb_get_history(e_, slot, firstBlock, nBlocks, out.data()));
         return out;
     }
+    // JuicyMeterPanel state of every clip after the render (src/shared/JuicyMeterPanel.cpp:9-34,54-71)
+    std::vector<jb_meter_stats> getMeterStatistics(int slot, int firstBlock, int nBlocks, int blockStride = 1)
+    {
+        std::vector<jb_meter_stats> out((size_t) nClips_);
+        check(jb_meter_statistics(e_, slot, firstBlock, nBlocks, blockStride, out.data()));
+        return out;
+    }
 
     int getNumClips() const { return nClips_; }
     jb_engine* handle() { return e_; }

@@ -80,6 +80,7 @@ def lib():
         "jb_enable_history": (ci, [vp, ci]),
         "jb_history_blocks": (ci, [vp]),
         "jb_get_history": (ci, [vp, ci, ci, ci, vp]),
+        "jb_meter_statistics": (ci, [vp, ci, ci, ci, ci, vp]),
         "jb_synth_fill": (ci, [vp, ci, cll, ci, ci, ci, cd, ctypes.c_uint, ci, vp]),
         "jb_synth_fill_host": (ci, [vp, ci, cll, ci, ci, ci, cd, ctypes.c_uint]),
         "jb_launch_count": (cll, []),
@@ -321,6 +322,16 @@ class BatchProcessor:
         out = np.zeros((n_blocks, self.n_clips, 16), dtype=np.float32)
         if n_blocks > 0:
             _check(lib().jb_get_history(self._h, self.slot(slot), int(first_block), int(n_blocks), out.ctypes.data))
+        return out
+
+    def meterStatistics(self, slot=0, first_block=0, n_blocks=None, block_stride=1):
+        """[n_clips][40] JuicyMeterPanel state after the render (jb_meter_stats field order): 8 smoothed bar
+        values, (min, max, avg) of the 10 tracked metrics, records fed."""
+        if n_blocks is None:
+            n_blocks = self.historyBlocks() - first_block
+        out = np.zeros((self.n_clips, 40), dtype=np.float32)
+        _check(lib().jb_meter_statistics(self._h, self.slot(slot), int(first_block), int(n_blocks), int(block_stride),
+                                         out.ctypes.data))
         return out
 
     def set_path(self, mode):

@@ -9,6 +9,7 @@
 // compile UNMODIFIED into oracle/_ref/ (see oracle/Makefile).  Only the members
 // those files touch are provided.  Numeric helpers follow SURVEY.md Appendix C.
 #pragma once
+#include <cstdio>
 
 #include <algorithm>
 #include <atomic>
@@ -98,6 +99,13 @@ public:
     String() = default;
     String(const char* s) : text(s != nullptr ? s : "") {}
     String(const std::string& s) : text(s) {}
+    String(float value, int decimals) // juce::String(double, numberOfDecimalPlaces); only the meter panel's labels use it
+    {
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "%.*f", decimals, (double) value);
+        text = buf;
+    }
+    String operator+(const char* s) const { return String(text + (s != nullptr ? s : "")); }
     bool operator==(const String& o) const { return text == o.text; }
     bool operator!=(const String& o) const { return text != o.text; }
     bool operator<(const String& o) const { return text < o.text; }

@@ -1130,3 +1130,71 @@ double jo_render_clips(void* vp, float* audio, long numClips, long numSamples, i
     }
     return seconds;
 }
+
+/* ------------------------------------------------------------------ meter panel */
+
+/* JuicyMeterPanel::smoothValue, src/shared/JuicyMeterPanel.cpp:3-7 */
+static float meter_smooth(float current, float target)
+{
+    const float alpha = target > current ? 0.28f : 0.12f;
+    return current + (target - current) * alpha;
+}
+
+typedef struct { float min, max, avg; int count; } MeterStats; /* JuicyMeterPanel.h:16-22 */
+
+/* JuicyMeterPanel::updateStats, src/shared/JuicyMeterPanel.cpp:54-71 */
+static void meter_update(MeterStats* s, float value)
+{
+    const float v = clampf(0.0f, 1.0f, value);
+    if (s->count == 0) {
+        s->min = v;
+        s->max = v;
+        s->avg = v;
+        s->count = 1;
+        return;
+    }
+    s->min = fmin2(s->min, v);
+    s->max = fmax2(s->max, v);
+    ++s->count;
+    const float n = (float) s->count;
+    s->avg += (v - s->avg) / n;
+}
+
+/* JuicyMeterPanel::setMetrics over a block-ordered history, src/shared/JuicyMeterPanel.cpp:9-34.
+ * Record layout: score 0, preScore 1, postScore 2, emphasis 3, coherence 4, synesthesia 5, fatigueRisk 6,
+ * repetitionDensity 7, punch 8, richness 9, clarity 10, width 11, monoSafety 12. */
+void jo_meter_run(const float* records, int n, float* out)
+{
+    /* `JuicinessMetrics metrics;` starts from the struct's defaults (JuicinessAnalyzer.h:6-21): monoSafety 1, rest 0 */
+    float preScore = 0.0f, postScore = 0.0f, score = 0.0f, punch = 0.0f, richness = 0.0f, clarity = 0.0f, width = 0.0f,
+          monoSafety = 1.0f;
+    MeterStats st[10];
+    for (int k = 0; k < 10; ++k) {
+        st[k].min = 1.0f; st[k].max = 0.0f; st[k].avg = 0.0f; st[k].count = 0;
+    }
+    static const int statField[10] = { 8, 9, 10, 11, 12, 3, 4, 5, 6, 7 };
+    for (int i = 0; i < n; ++i) {
+        const float* r = records + 16 * i;
+        const float newPre = r[1] > 0.0f ? r[1] : r[0];
+        const float newPost = r[2] > 0.0f ? r[2] : r[0];
+        preScore = meter_smooth(preScore, newPre);
+        postScore = meter_smooth(postScore, newPost);
+        for (int k = 0; k < 10; ++k)
+            meter_update(&st[k], r[statField[k]]);
+        score = meter_smooth(score, newPost);
+        punch = meter_smooth(punch, r[8]);
+        richness = meter_smooth(richness, r[9]);
+        clarity = meter_smooth(clarity, r[10]);
+        width = meter_smooth(width, r[11]);
+        monoSafety = meter_smooth(monoSafety, r[12]);
+    }
+    out[0] = preScore; out[1] = postScore; out[2] = score;
+    out[3] = punch; out[4] = richness; out[5] = clarity; out[6] = width; out[7] = monoSafety;
+    for (int k = 0; k < 10; ++k) {
+        out[8 + 3 * k] = st[k].min;
+        out[9 + 3 * k] = st[k].max;
+        out[10 + 3 * k] = st[k].avg;
+    }
+    out[38] = (float) st[0].count;
+    out[39] = 0.0f;
+}

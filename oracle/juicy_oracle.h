@@ -46,6 +46,12 @@ void jo_latest(void* p, float* rec16);
 double jo_render_clips(void* p, float* audio, long numClips, long numSamples, int blockSize,
                        double sampleRate, float* lastRecords);
 
+/* Meter-panel statistics over a render: feed n records ([n][16], JuicinessMetrics field order)
+ * to JuicyMeterPanel::setMetrics in block order; out = 40 floats: smoothed preScore, postScore, score, punch,
+ * richness, clarity, width, monoSafety; (min, max, avg) of punch, richness, clarity, width, monoSafety, emphasis,
+ * coherence, synesthesia, fatigue, repetition; sample count; pad.  Same layout as ref_meter_run. */
+void jo_meter_run(const float* records, int n, float* out);
+
 #ifdef __cplusplus
 }
 #endif

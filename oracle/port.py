@@ -36,3 +36,16 @@ class PortPlugin(refhost.OraclePlugin):
 
 def run_chain(chain, audio, **kw):
     return refhost.run_chain(chain, audio, cls=PortPlugin, **kw)
+
+
+def meter_run(records):
+    """JuicyMeterPanel statistics (40 floats) after feeding [n][16] records in block order (jo_meter_run)."""
+    import numpy as np
+    rec = np.ascontiguousarray(records, dtype=np.float32)
+    out = np.zeros(40, dtype=np.float32)
+    fn = ctypes.CDLL(LIB_PATH).jo_meter_run
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    fn.restype = None
+    lib()
+    fn(rec.ctypes.data, int(rec.shape[0]), out.ctypes.data)
+    return out

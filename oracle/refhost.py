@@ -185,3 +185,18 @@ def run_chain(chain, audio, channels=2, sample_rate=48000.0, block_size=512, pro
         hists.append(h)
         p.close()
     return x, hists
+
+
+def meter_run(records):
+    """The reference's own JuicyMeterPanel (oracle/_ref/libjuicy_ref_MeterPanel.so) fed [n][16] records."""
+    rec = np.ascontiguousarray(records, dtype=np.float32)
+    out = np.zeros(40, dtype=np.float32)
+    fn = ctypes.CDLL(os.path.join(REF_DIR, "libjuicy_ref_MeterPanel.so")).ref_meter_run
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    fn.restype = None
+    fn(rec.ctypes.data, int(rec.shape[0]), out.ctypes.data)
+    return out
+
+
+def meter_available():
+    return os.path.exists(os.path.join(REF_DIR, "libjuicy_ref_MeterPanel.so"))
