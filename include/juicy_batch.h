@@ -112,6 +112,25 @@ int jb_set_param(jb_engine* e, int slot, const char* id, float plain_value);
 /* param->setValueNotifyingHost(normalised) */
 int jb_set_param_normalised(jb_engine* e, int slot, const char* id, float normalised);
 
+/* Per-clip parameters and per-block automation.  The reference re-reads its parameters at the top of
+ * every processBlock (37 getRawParameterValue sites, e.g. JuicyPunch/PluginProcessor.cpp:71-78), so a host can give every
+ * plugin instance its own settings and automate them between callbacks.  Here:
+ *  - jb_set_param_clips / jb_set_program_clips give clips [first_clip, first_clip + n_clips) their own values (first_clip =
+ *    JB_ALL_CLIPS: every clip; jb_set_param & co. always address every clip).  Clips with identical settings share a
+ *    parameter set and render in one launch; jb_num_param_sets reports how many distinct sets are in use.
+ *  - jb_get_param_clip reads one clip's value (jb_get_param reads parameter set 0, the engine-wide default).
+ *  - jb_schedule_param makes a change take effect at the top of absolute block `at_block` (counted in host blocks since
+ *    jb_prepare / jb_reset, the index jb_get_history uses): the equivalent of the host calling setValueNotifyingHost between
+ *    two processBlock callbacks inside one jb_process / jb_process_host render.  Applied changes persist like any other
+ *    parameter change; jb_prepare / jb_reset / jb_clear_schedule drop what is still pending. */
+int jb_set_param_clips(jb_engine* e, int slot, const char* id, float plain_value, int first_clip, int n_clips);
+int jb_set_program_clips(jb_engine* e, int slot, int index, int first_clip, int n_clips);
+int jb_get_param_clip(const jb_engine* e, int slot, const char* id, int clip, float* out);
+int jb_num_param_sets(const jb_engine* e);
+int jb_schedule_param(jb_engine* e, int slot, const char* id, long long at_block, float plain_value, int first_clip,
+                      int n_clips);
+int jb_clear_schedule(jb_engine* e);
+
 /* Programs: getNumPrograms / getCurrentProgram / setCurrentProgram / getProgramName
  * (e.g. JuicyWidth/PluginProcessor.cpp:171-210). */
 int jb_num_programs(const jb_engine* e, int slot);
@@ -186,6 +205,16 @@ int jb_synth_fill_host(float* h_audio, int kind, long long first_clip, int n_cli
 #define JB_PATH_LANE 1
 #define JB_PATH_COOP 2
 int jb_set_path(jb_engine* e, int mode);
+/* Per-sample std::tanh / std::pow of Saturator and Punch (JuicySaturator/PluginProcessor.cpp:92, JuicyPunch/
+ * PluginProcessor.cpp:100,106).  JB_MATH_FAST: special-function-unit based, within 3e-6 relative of the C library (the
+ * stated sample tolerance for the plugin itself).  JB_MATH_EXACT: the C library's own algorithms restated (fdlibm tanhf,
+ * glibc powf), bit-identical to the reference built against glibc 2.28 - 2.39, about 1.5x the arithmetic.  JB_MATH_AUTO
+ * (default): exact when a JuicyTexture comes later in the chain -- its metal / wood / plastic resonators amplify a 1e-6
+ * input difference ~200x -- fast otherwise.  The cooperative kernel only runs in fast mode. */
+#define JB_MATH_AUTO 0
+#define JB_MATH_EXACT 1
+#define JB_MATH_FAST 2
+int jb_set_math_mode(jb_engine* e, int mode);
 /* Launches of each render kernel by this engine so far (either pointer may be null). */
 int jb_path_launches(const jb_engine* e, long long* cooperative, long long* lane_per_clip);
 

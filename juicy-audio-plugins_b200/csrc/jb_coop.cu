@@ -943,7 +943,7 @@ size_t jbk_coop_scratch_bytes(int chainLen, int numSMs)
 // in front, host block <= 512, everything 16-byte aligned, the Width ring long enough for a step.)
 int jbk_coop_supported(const ProcArgs* a)
 {
-    if (a->chainLen < 1 || a->chainLen > CO_MAXCHAIN || a->nCh != 2)
+    if (a->chainLen < 1 || a->chainLen > CO_MAXCHAIN || a->nCh != 2 || a->clipMap != nullptr)
         return 0;
     if (a->blockSize > CO_BLOCKMAX || a->blockSize % 4 != 0 || a->nSamples % 4 != 0 || a->rowPitch % 4 != 0)
         return 0;

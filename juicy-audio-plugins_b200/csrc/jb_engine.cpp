@@ -96,6 +96,7 @@ struct jb_engine {
     bool ringClipMajor = false;    // Width ring layout: [clip][ringLen] (cooperative-capable chains) or [ringLen][clip]
     bool coopCapable = false;      // chain made of plugins the cooperative kernel implements
     int numSMs = 0;
+    int mathMode = 0;              // 0 auto (exact where a Texture follows a Saturator / Punch), 1 exact, 2 fast
     int pathMode = 0;              // 0 auto, 1 force lane-per-clip, 2 force cooperative (fails if unsupported)
     long long coopLaunches = 0, laneLaunches = 0;
     int ringLen = 0, waveLen = 0;
@@ -112,6 +113,24 @@ struct jb_engine {
     size_t stageBytes = 0;
 
     std::vector<float> hostScratch;
+
+    // Per-clip parameters.  `params` is parameter set 0; clips given other values use a set of
+    // `variants` (set k > 0 = variants[k - 1]); clipSet[clip] = set index (empty: every clip uses set 0).  Clips of one
+    // set render in one launch: a contiguous clip range directly, a scattered set through a device clip map.
+    struct Group { int set; int first; int count; long long mapOffset; }; // first < 0: mapped, mapOffset into clipMapHost
+    std::vector<std::vector<jb::ParamSet>> variants;
+    std::vector<int> clipSet;
+    std::vector<Group> groups;
+    std::vector<int> clipMapHost;
+    int* dClipMap = nullptr;
+    bool groupsDirty = false;
+    // Per-block automation: parameter changes taking effect at the start of an absolute block index
+    struct AutoEvent { long long block; int slot; int index; float value; int first; int count; };
+    std::vector<AutoEvent> schedule; // kept sorted by block (stable)
+    static constexpr int kGroupStreams = 8;
+    cudaStream_t groupStream[kGroupStreams] = {};
+    cudaEvent_t groupJoin[kGroupStreams] = {};
+    cudaEvent_t groupFork = nullptr;
 
     // CUDA-event pairs around every render-kernel launch (jb_kernel_time_ms)
     std::vector<cudaEvent_t> timingEvents; // start0, stop0, start1, stop1, ...
@@ -157,6 +176,17 @@ void freeDevice(jb_engine* e)
     cudaFree(e->dRing);
     cudaFree(e->dWave);
     cudaFree(e->dCoopScratch);
+    cudaFree(e->dClipMap);
+    e->dClipMap = nullptr;
+    for (int i = 0; i < jb_engine::kGroupStreams; ++i) {
+        if (e->groupStream[i]) cudaStreamDestroy(e->groupStream[i]);
+        if (e->groupJoin[i]) cudaEventDestroy(e->groupJoin[i]);
+        e->groupStream[i] = nullptr;
+        e->groupJoin[i] = nullptr;
+    }
+    if (e->groupFork) cudaEventDestroy(e->groupFork);
+    e->groupFork = nullptr;
+    e->groupsDirty = true;
     e->dState = e->dLatest = e->dHist = e->dRing = e->dWave = e->dCoopScratch = nullptr;
     for (int i = 0; i < 3; ++i) {
         cudaFree(e->dStage[i]);
@@ -265,11 +295,12 @@ int resetState(jb_engine* e)
     if (e->dHist)
         JB_CUDA(cudaMemsetAsync(e->dHist, 0, sizeof(float) * (size_t) e->histMaxBlocks * e->chain.size() * JBK_REC * (size_t) e->clipPitch, e->stream));
     e->blocksDone = 0;
+    e->schedule.clear(); // scheduled changes are addressed by block index since this prepare / reset
     return JB_OK;
 }
 
-int buildArgs(jb_engine* e, ProcArgs& a, const float* dIn, float* dOut, int nSamples, int nClips, long long clipOffset,
-              long long rowPitch = 0)
+int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params, const float* dIn, float* dOut, int nSamples,
+              int nClips, long long clipOffset, long long rowPitch = 0)
 {
     std::memset(&a, 0, sizeof a);
     a.in = dIn;
@@ -298,11 +329,23 @@ int buildArgs(jb_engine* e, ProcArgs& a, const float* dIn, float* dOut, int nSam
     for (int k : e->chain)
         if (k == jb::kPunch || k == jb::kTexture || k == jb::kMotion)
             a.octets = 0;
+    {   // Saturator / Punch transcendentals: the MUFU-based ones are within 3e-6 of the reference, which Texture's metal /
+        // wood / plastic resonators amplify ~200x; with a Texture further down the chain they run the C library's own
+        // algorithms (jb_libm.h) so that its input is the reference's, bit for bit.
+        bool shaperSeen = false, resonatorAfterShaper = false;
+        for (int k : e->chain) {
+            if (k == jb::kPunch || k == jb::kSaturator)
+                shaperSeen = true;
+            if (k == jb::kTexture && shaperSeen)
+                resonatorAfterShaper = true;
+        }
+        a.exactMath = e->mathMode == 1 || (e->mathMode == 0 && resonatorAfterShaper) ? 1 : 0;
+    }
     a.ana = jb::makeAnaCoef(e->sampleRate);
     for (size_t s = 0; s < e->chain.size(); ++s) {
         a.slot[s].kind = e->chain[s];
         a.slot[s].stateBase = e->stateBase[s];
-        jb::makeSlotCoef(e->params[s], e->sampleRate, &a.slot[s].c);
+        jb::makeSlotCoef(params[s], e->sampleRate, &a.slot[s].c);
     }
     return JB_OK;
 }
@@ -323,8 +366,8 @@ int drainTiming(jb_engine* e)
     return JB_OK;
 }
 
-// One render-kernel launch bracketed by timing events on the engine's stream.
-int launchProcess(jb_engine* e, const ProcArgs& a)
+// Timing-event pair for one render on the engine's stream (jb_kernel_time_ms).
+int timingPair(jb_engine* e, cudaEvent_t* start, cudaEvent_t* stop)
 {
     if (e->timingUsed + 2 > e->timingEvents.size()) {
         if (e->timingEvents.size() >= 256) {
@@ -338,10 +381,18 @@ int launchProcess(jb_engine* e, const ProcArgs& a)
             }
         }
     }
-    cudaEvent_t start = e->timingEvents[e->timingUsed], stop = e->timingEvents[e->timingUsed + 1];
+    *start = e->timingEvents[e->timingUsed];
+    *stop = e->timingEvents[e->timingUsed + 1];
+    return JB_OK;
+}
+
+// The render kernel(s) of one ProcArgs on `stream`, untimed.  allowCoop: the cooperative kernel may be chosen (it owns
+// engine-wide scratch, so concurrent launches of several parameter sets stay on the lane kernels).
+int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool allowCoop)
+{
     // Path choice: the cooperative (time-parallel) kernel when the chain and the call's shape allow it and
-    // the batch is too small to fill the GPU with one lane per clip; the lane-per-clip kernel otherwise.
-    bool coop = e->coopCapable && e->dCoopScratch != nullptr && jbk_coop_supported(&a) != 0;
+    // the batch is too small to fill the GPU with one lane per clip; the lane-per-clip kernels otherwise.
+    bool coop = allowCoop && a.exactMath == 0 && e->coopCapable && e->dCoopScratch != nullptr && jbk_coop_supported(&a) != 0;
     if (e->pathMode == 1)
         coop = false;
     else if (e->pathMode == 2 && !coop)
@@ -362,41 +413,263 @@ int launchProcess(jb_engine* e, const ProcArgs& a)
         if (a.nClips > limit)
             coop = false;
     }
-    JB_CUDA(cudaEventRecord(start, e->stream));
     if (coop) {
-        if (jbk_launch_coop(&a, e->dCoopScratch, e->numSMs, e->stream) != 0)
+        if (jbk_launch_coop(&a, e->dCoopScratch, e->numSMs, stream) != 0)
             return fail(JB_ERR_CUDA, "%s", jbk_coop_last_error());
         ++e->coopLaunches;
-    } else {
-        // Lane kernel, chain of several plugins: one launch per plugin over the whole call (plugin s + 1 only
-        // needs plugin s's output of the same block, and every plugin blocks identically, so plugin-by-plugin
-        // equals block-by-block).  A single-plugin launch is small code with no spills and picks its own
-        // 8-samples-per-trip mode; the fused 8-sweep kernel took 2.5x the sum of its parts.
-        // Measured (profiles/r01_survey_chain.txt): 7-plugin chain on 32768 clips 424 -> 161 ms; below ~20k clips
-        // the render is latency-bound and the two modes tie.  JB_LANE_SPLIT=0/1 forces a mode.
-        const char* splitEnv = std::getenv("JB_LANE_SPLIT");
-        const int splitMode = splitEnv == nullptr ? -1 : std::atoi(splitEnv);
-        const bool splitChains = splitMode < 0 ? a.nClips >= 20480 : splitMode != 0;
-        const int L = a.chainLen;
-        if (L > 1 && splitChains) {
-            for (int s = 0; s < L; ++s) {
-                ProcArgs one = a;
-                one.in = s == 0 ? a.in : a.out;
-                one.chainLen = 1;
-                one.slot[0] = a.slot[s];
-                one.recSlotBase = s;
-                one.recChainLen = L;
-                one.octets = a.nClips >= 32768 && !(one.slot[0].kind == jb::kPunch || one.slot[0].kind == jb::kTexture || one.slot[0].kind == jb::kMotion);
-                if (jbk_launch_process(&one, e->stream) != 0)
-                    return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
-            }
-        } else if (jbk_launch_process(&a, e->stream) != 0) {
-            return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
-        }
-        ++e->laneLaunches;
+        return JB_OK;
     }
+    // Lane kernels, chain of several plugins: one launch per plugin over the whole call (plugin s + 1 only needs
+    // plugin s's output of the same block, and every plugin blocks identically, so plugin-by-plugin equals
+    // block-by-block).  Each launch is that plugin's own kernel (jb_single_kernel: coefficients as constant-bank
+    // operands, a few thousand instructions, its own register budget); the fused generic kernel spills and re-reads
+    // its coefficients per sample.  Measured (profiles/r01_s6_survey_single.txt): 7-plugin chain 32768 clips
+    // 424 (fused) -> 125 ms, 4096 clips 83 -> 68 ms.  JB_LANE_SPLIT=0 forces the fused kernel (tests keep it exact).
+    const char* splitEnv = std::getenv("JB_LANE_SPLIT");
+    const bool splitChains = a.exactMath != 0 || splitEnv == nullptr || std::atoi(splitEnv) != 0;
+    const int L = a.chainLen;
+    if (L > 1 && splitChains) {
+        for (int s = 0; s < L; ++s) {
+            ProcArgs one = a;
+            one.in = s == 0 ? a.in : a.out;
+            one.chainLen = 1;
+            one.slot[0] = a.slot[s];
+            one.recSlotBase = s;
+            one.recChainLen = L;
+            one.octets = a.clipMap == nullptr && a.nClips >= 32768
+                         && !(one.slot[0].kind == jb::kPunch || one.slot[0].kind == jb::kTexture || one.slot[0].kind == jb::kMotion);
+            if (jbk_launch_process(&one, stream) != 0)
+                return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
+        }
+    } else if (jbk_launch_process(&a, stream) != 0) {
+        return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
+    }
+    ++e->laneLaunches;
+    return JB_OK;
+}
+
+// One render bracketed by timing events on the engine's stream.
+int launchProcess(jb_engine* e, const ProcArgs& a)
+{
+    cudaEvent_t start = nullptr, stop = nullptr;
+    if (int rc = timingPair(e, &start, &stop))
+        return rc;
+    JB_CUDA(cudaEventRecord(start, e->stream));
+    if (int rc = launchKernels(e, a, e->stream, true))
+        return rc;
     JB_CUDA(cudaEventRecord(stop, e->stream));
     e->timingUsed += 2;
+    return JB_OK;
+}
+
+const std::vector<jb::ParamSet>& paramsOfSet(const jb_engine* e, int set)
+{
+    return set == 0 ? e->params : e->variants[(size_t) set - 1];
+}
+
+// Merge identical parameter sets, drop unused ones, fall back to the single-set state when every clip uses set 0.
+void normalizeSets(jb_engine* e)
+{
+    e->groupsDirty = true;
+    if (e->clipSet.empty()) {
+        e->variants.clear();
+        return;
+    }
+    const int nSets = 1 + (int) e->variants.size();
+    std::vector<int> canon((size_t) nSets);
+    for (int k = 0; k < nSets; ++k) {
+        canon[(size_t) k] = k;
+        for (int j = 0; j < k; ++j)
+            if (canon[(size_t) j] == j && paramsOfSet(e, j) == paramsOfSet(e, k)) {
+                canon[(size_t) k] = j;
+                break;
+            }
+    }
+    std::vector<char> used((size_t) nSets, 0);
+    for (int& c : e->clipSet) {
+        c = canon[(size_t) c];
+        used[(size_t) c] = 1;
+    }
+    std::vector<int> renum((size_t) nSets, 0);
+    std::vector<std::vector<jb::ParamSet>> kept;
+    for (int k = 1; k < nSets; ++k)
+        if (used[(size_t) k]) {
+            kept.push_back(std::move(e->variants[(size_t) k - 1]));
+            renum[(size_t) k] = (int) kept.size();
+        }
+    e->variants = std::move(kept);
+    bool anyVariant = false;
+    for (int& c : e->clipSet) {
+        c = renum[(size_t) c];
+        anyVariant = anyVariant || c != 0;
+    }
+    if (!anyVariant)
+        e->clipSet.clear();
+}
+
+// Apply `change` to the parameters of clips [first, first + count) (count < 0: every clip, set 0 included).
+template <class F>
+void changeParams(jb_engine* e, int first, int count, F change)
+{
+    if (count < 0 || (first == 0 && count == e->nClips)) {
+        change(e->params);
+        for (auto& v : e->variants)
+            change(v);
+        normalizeSets(e);
+        return;
+    }
+    if (e->clipSet.empty())
+        e->clipSet.assign((size_t) e->nClips, 0);
+    std::vector<int> newOf(1 + e->variants.size(), -1);
+    for (int c = first; c < first + count; ++c) {
+        const int old = e->clipSet[(size_t) c];
+        if (newOf[(size_t) old] < 0) {
+            std::vector<jb::ParamSet> copy = paramsOfSet(e, old);
+            change(copy);
+            e->variants.push_back(std::move(copy));
+            newOf[(size_t) old] = (int) e->variants.size();
+        }
+        e->clipSet[(size_t) c] = newOf[(size_t) old];
+    }
+    normalizeSets(e);
+}
+
+int rebuildGroups(jb_engine* e)
+{
+    e->groups.clear();
+    e->clipMapHost.clear();
+    e->groupsDirty = false;
+    if (e->clipSet.empty())
+        return JB_OK;
+    const int nSets = 1 + (int) e->variants.size();
+    std::vector<std::vector<int>> members((size_t) nSets);
+    for (int c = 0; c < e->nClips; ++c)
+        members[(size_t) e->clipSet[(size_t) c]].push_back(c);
+    for (int k = 0; k < nSets; ++k) {
+        const std::vector<int>& m = members[(size_t) k];
+        if (m.empty())
+            continue;
+        if (m.back() - m.front() + 1 == (int) m.size()) {
+            e->groups.push_back({ k, m.front(), (int) m.size(), -1 });
+        } else {
+            e->groups.push_back({ k, -1, (int) m.size(), (long long) e->clipMapHost.size() });
+            e->clipMapHost.insert(e->clipMapHost.end(), m.begin(), m.end());
+        }
+    }
+    if (!e->clipMapHost.empty()) {
+        if (e->dClipMap == nullptr)
+            JB_CUDA(cudaMalloc(&e->dClipMap, sizeof(int) * (size_t) e->nClips));
+        JB_CUDA(cudaMemcpyAsync(e->dClipMap, e->clipMapHost.data(), sizeof(int) * e->clipMapHost.size(), cudaMemcpyHostToDevice, e->stream));
+        JB_CUDA(cudaStreamSynchronize(e->stream)); // clipMapHost may change before the copy would otherwise run
+    }
+    return JB_OK;
+}
+
+// Render ns samples of clips [c0, c0 + nc); dIn / dOut point at clip c0's first sample of the range.  One launch per
+// parameter set present in the range.
+int renderClips(jb_engine* e, const float* dIn, float* dOut, int ns, int nc, long long c0, long long rowPitch)
+{
+    if (e->clipSet.empty()) {
+        ProcArgs a;
+        buildArgs(e, a, e->params, dIn, dOut, ns, nc, c0, rowPitch);
+        return launchProcess(e, a);
+    }
+    if (e->groupsDirty)
+        if (int rc = rebuildGroups(e))
+            return rc;
+    // The sets' launches touch disjoint clips, and each is usually far too small to fill the GPU (a latency-bound walk
+    // through time), so they go out on a small pool of side streams between a fork and a join on the engine's stream.
+    const long long clipStride = (long long) e->nCh * rowPitch;
+    constexpr int kPool = jb_engine::kGroupStreams;
+    if (e->groupStream[0] == nullptr) {
+        for (int i = 0; i < kPool; ++i) {
+            JB_CUDA(cudaStreamCreateWithFlags(&e->groupStream[i], cudaStreamNonBlocking));
+            JB_CUDA(cudaEventCreateWithFlags(&e->groupJoin[i], cudaEventDisableTiming));
+        }
+        JB_CUDA(cudaEventCreateWithFlags(&e->groupFork, cudaEventDisableTiming));
+    }
+    static const bool forceSerial = [] { const char* v = std::getenv("JB_GROUP_SERIAL"); return v != nullptr && std::atoi(v) != 0; }();
+    // ... as long as all of them fit the GPU together (the heavy kernels hold at most 8 warps per SM): beyond that the
+    // launches queue behind each other's tails and one after the other is faster (32768 clips in 5 Texture materials:
+    // 141 ms serial, 192 ms concurrent; 8192 clips: 133 ms serial, 80 ms concurrent -- profiles/r01_s6_survey_single.txt)
+    const long long warpsInCall = (nc + 31) / 32 + (long long) e->groups.size();
+    const bool serial = forceSerial || e->pathMode == 2 || e->groups.size() < 2 || warpsInCall > (long long) e->numSMs * 6;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    if (int rc = timingPair(e, &start, &stop))
+        return rc;
+    JB_CUDA(cudaEventRecord(start, e->stream));
+    if (!serial)
+        JB_CUDA(cudaEventRecord(e->groupFork, e->stream));
+    bool usedStream[kPool] = {};
+    int next = 0;
+    for (const jb_engine::Group& g : e->groups) {
+        ProcArgs a;
+        if (g.first >= 0) {
+            const long long lo = std::max<long long>(g.first, c0), hi = std::min<long long>((long long) g.first + g.count, c0 + nc);
+            if (lo >= hi)
+                continue;
+            buildArgs(e, a, paramsOfSet(e, g.set), dIn + (lo - c0) * clipStride, dOut + (lo - c0) * clipStride, ns, (int) (hi - lo), lo,
+                      rowPitch);
+        } else {
+            const int* m = e->clipMapHost.data() + g.mapOffset;
+            const int* i0 = std::lower_bound(m, m + g.count, (int) c0);
+            const int* i1 = std::lower_bound(m, m + g.count, (int) (c0 + nc));
+            if (i0 >= i1)
+                continue;
+            // absolute clip numbers index the state arrays; the audio pointers are moved back to where clip 0 would be
+            buildArgs(e, a, paramsOfSet(e, g.set), dIn - c0 * clipStride, dOut - c0 * clipStride, ns, (int) (i1 - i0), 0, rowPitch);
+            a.clipMap = e->dClipMap + g.mapOffset + (i0 - m);
+            a.octets = 0;
+        }
+        cudaStream_t st = e->stream;
+        if (!serial) {
+            st = e->groupStream[next];
+            if (!usedStream[next]) {
+                JB_CUDA(cudaStreamWaitEvent(st, e->groupFork, 0));
+                usedStream[next] = true;
+            }
+            next = (next + 1) % kPool;
+        }
+        if (int rc = launchKernels(e, a, st, serial))
+            return rc;
+    }
+    if (!serial)
+        for (int i = 0; i < kPool; ++i)
+            if (usedStream[i]) {
+                JB_CUDA(cudaEventRecord(e->groupJoin[i], e->groupStream[i]));
+                JB_CUDA(cudaStreamWaitEvent(e->stream, e->groupJoin[i], 0));
+            }
+    JB_CUDA(cudaEventRecord(stop, e->stream));
+    e->timingUsed += 2;
+    return JB_OK;
+}
+
+// The same with the automation schedule: the range starts at absolute block firstBlock; parameter changes scheduled for
+// a block take effect before that block's processBlock, exactly like a host that calls setValueNotifyingHost between
+// callbacks, so the render is cut there.  Consumes the events it applies.
+int renderAutomated(jb_engine* e, const float* dIn, float* dOut, int ns, int nc, long long c0, long long rowPitch, long long firstBlock)
+{
+    const int B = e->blockSize;
+    const long long endBlock = firstBlock + (ns + B - 1) / B;
+    long long cur = firstBlock;
+    while (cur < endBlock) {
+        size_t applied = 0;
+        while (applied < e->schedule.size() && e->schedule[applied].block <= cur) {
+            const jb_engine::AutoEvent& ev = e->schedule[applied];
+            changeParams(e, ev.first, ev.count, [&](std::vector<jb::ParamSet>& p) { p[(size_t) ev.slot].setPlain(ev.index, ev.value); });
+            ++applied;
+        }
+        e->schedule.erase(e->schedule.begin(), e->schedule.begin() + (long) applied);
+        long long next = endBlock;
+        if (!e->schedule.empty() && e->schedule.front().block < next)
+            next = e->schedule.front().block;
+        const long long t0 = (cur - firstBlock) * B;
+        const int len = (int) std::min<long long>(ns - t0, (next - cur) * B);
+        e->blocksDone = cur; // history index of this segment's first block
+        if (int rc = renderClips(e, dIn + t0, dOut + t0, len, nc, c0, rowPitch))
+            return rc;
+        cur = next;
+    }
     return JB_OK;
 }
 
@@ -598,7 +871,7 @@ int jb_set_param(jb_engine* e, int slot, const char* id, float plain_value)
     int idx = -1;
     if (int rc = findParam(e, slot, id, &idx))
         return rc;
-    e->params[(size_t) slot].setPlain(idx, plain_value);
+    changeParams(e, 0, -1, [&](std::vector<jb::ParamSet>& p) { p[(size_t) slot].setPlain(idx, plain_value); });
     return JB_OK;
 }
 
@@ -607,7 +880,92 @@ int jb_set_param_normalised(jb_engine* e, int slot, const char* id, float normal
     int idx = -1;
     if (int rc = findParam(e, slot, id, &idx))
         return rc;
-    e->params[(size_t) slot].setNormalised(idx, normalised);
+    changeParams(e, 0, -1, [&](std::vector<jb::ParamSet>& p) { p[(size_t) slot].setNormalised(idx, normalised); });
+    return JB_OK;
+}
+
+static int checkClipRange(const jb_engine* e, int first_clip, int n_clips)
+{
+    if (first_clip == JB_ALL_CLIPS)
+        return JB_OK;
+    if (first_clip < 0 || n_clips < 1 || (long long) first_clip + n_clips > e->nClips)
+        return fail(JB_ERR_ARG, "clip range [%d, %d) outside the engine's %d clips", first_clip, first_clip + n_clips, e->nClips);
+    return JB_OK;
+}
+
+int jb_set_param_clips(jb_engine* e, int slot, const char* id, float plain_value, int first_clip, int n_clips)
+{
+    int idx = -1;
+    if (int rc = findParam(e, slot, id, &idx))
+        return rc;
+    if (int rc = checkClipRange(e, first_clip, n_clips))
+        return rc;
+    changeParams(e, first_clip == JB_ALL_CLIPS ? 0 : first_clip, first_clip == JB_ALL_CLIPS ? -1 : n_clips,
+                 [&](std::vector<jb::ParamSet>& p) { p[(size_t) slot].setPlain(idx, plain_value); });
+    return JB_OK;
+}
+
+int jb_set_program_clips(jb_engine* e, int slot, int index, int first_clip, int n_clips)
+{
+    if (int rc = checkSlot(e, slot))
+        return rc;
+    if (int rc = checkClipRange(e, first_clip, n_clips))
+        return rc;
+    changeParams(e, first_clip == JB_ALL_CLIPS ? 0 : first_clip, first_clip == JB_ALL_CLIPS ? -1 : n_clips,
+                 [&](std::vector<jb::ParamSet>& p) { p[(size_t) slot].setProgram(index); });
+    return JB_OK;
+}
+
+int jb_get_param_clip(const jb_engine* e, int slot, const char* id, int clip, float* out)
+{
+    int idx = -1;
+    if (int rc = findParam(e, slot, id, &idx))
+        return rc;
+    if (out == nullptr || clip < 0 || clip >= e->nClips)
+        return fail(JB_ERR_ARG, "jb_get_param_clip: bad clip %d or null output", clip);
+    const int set = e->clipSet.empty() ? 0 : e->clipSet[(size_t) clip];
+    *out = paramsOfSet(e, set)[(size_t) slot].raw(idx);
+    return JB_OK;
+}
+
+int jb_num_param_sets(const jb_engine* e)
+{
+    if (checkEngine(e) != JB_OK)
+        return JB_ERR_ARG;
+    if (e->clipSet.empty())
+        return 1;
+    std::vector<char> used(1 + e->variants.size(), 0);
+    int n = 0;
+    for (int c : e->clipSet)
+        if (!used[(size_t) c]) {
+            used[(size_t) c] = 1;
+            ++n;
+        }
+    return n;
+}
+
+int jb_schedule_param(jb_engine* e, int slot, const char* id, long long at_block, float plain_value, int first_clip, int n_clips)
+{
+    int idx = -1;
+    if (int rc = findParam(e, slot, id, &idx))
+        return rc;
+    if (int rc = checkClipRange(e, first_clip, n_clips))
+        return rc;
+    if (at_block < e->blocksDone)
+        return fail(JB_ERR_ARG, "jb_schedule_param: block %lld has already been rendered (%lld done)", at_block, e->blocksDone);
+    jb_engine::AutoEvent ev { at_block, slot, idx, plain_value, first_clip == JB_ALL_CLIPS ? 0 : first_clip,
+                              first_clip == JB_ALL_CLIPS ? -1 : n_clips };
+    auto pos = std::upper_bound(e->schedule.begin(), e->schedule.end(), ev,
+                                [](const jb_engine::AutoEvent& a, const jb_engine::AutoEvent& b) { return a.block < b.block; });
+    e->schedule.insert(pos, ev);
+    return JB_OK;
+}
+
+int jb_clear_schedule(jb_engine* e)
+{
+    if (int rc = checkEngine(e))
+        return rc;
+    e->schedule.clear();
     return JB_OK;
 }
 
@@ -618,7 +976,7 @@ int jb_set_program(jb_engine* e, int slot, int index)
 {
     if (int rc = checkSlot(e, slot))
         return rc;
-    e->params[(size_t) slot].setProgram(index);
+    changeParams(e, 0, -1, [&](std::vector<jb::ParamSet>& p) { p[(size_t) slot].setProgram(index); });
     return JB_OK;
 }
 
@@ -670,9 +1028,10 @@ int jb_process(jb_engine* e, const float* d_in, float* d_out, int n_samples)
         return fail(JB_ERR_ARG, "jb_process: negative n_samples");
     if (n_samples == 0)
         return JB_OK;
-    ProcArgs a;
-    buildArgs(e, a, d_in, d_out, n_samples, e->nClips, 0);
-    if (int rc = launchProcess(e, a))
+    const long long blocksBase = e->blocksDone;
+    const int rc = renderAutomated(e, d_in, d_out, n_samples, e->nClips, 0, n_samples, blocksBase);
+    e->blocksDone = blocksBase;
+    if (rc != JB_OK)
         return rc;
     e->blocksDone += (n_samples + e->blockSize - 1) / e->blockSize;
     return JB_OK;
@@ -738,7 +1097,20 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
 
     const long long blocksBase = e->blocksDone;
     int rcLaunch = JB_OK;
+    // every pass walks the same stretch of time, so each starts from the parameters and schedule the call began with
+    const bool replay = nPasses > 1 && !e->schedule.empty();
+    const auto params0 = replay ? e->params : std::vector<jb::ParamSet>();
+    const auto variants0 = replay ? e->variants : std::vector<std::vector<jb::ParamSet>>();
+    const auto clipSet0 = replay ? e->clipSet : std::vector<int>();
+    const auto schedule0 = replay ? e->schedule : std::vector<jb_engine::AutoEvent>();
     for (int pass = 0; pass < nPasses && rcLaunch == JB_OK; ++pass) {
+        if (replay && pass > 0) {
+            e->params = params0;
+            e->variants = variants0;
+            e->clipSet = clipSet0;
+            e->schedule = schedule0;
+            e->groupsDirty = true;
+        }
         const long long c0 = (long long) pass * passClips;
         const int nc = (int) std::min<long long>(passClips, e->nClips - c0);
         float* dBuf = e->dStage[pass % nBuffers];
@@ -756,10 +1128,7 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
                                       cudaMemcpyHostToDevice, e->copyIn));
             JB_CUDA(cudaEventRecord(evIn, e->copyIn));
             JB_CUDA(cudaStreamWaitEvent(e->stream, evIn, 0));
-            ProcArgs a;
-            e->blocksDone = blocksBase + firstBlock; // history index of the slice's first block
-            buildArgs(e, a, dBuf + t0, dBuf + t0, ns, nc, c0, n_samples);
-            if ((rcLaunch = launchProcess(e, a)) != JB_OK)
+            if ((rcLaunch = renderAutomated(e, dBuf + t0, dBuf + t0, ns, nc, c0, n_samples, blocksBase + firstBlock)) != JB_OK)
                 break;
             JB_CUDA(cudaEventRecord(evDone, e->stream));
             JB_CUDA(cudaStreamWaitEvent(e->copyOut, evDone, 0));
@@ -893,6 +1262,16 @@ int jb_meter_statistics(jb_engine* e, int slot, int first_block, int n_blocks, i
     for (int c = 0; c < e->nClips; ++c)
         for (int f = 0; f < JBK_METER; ++f)
             o[(size_t) c * JBK_METER + f] = e->hostScratch[(size_t) f * (size_t) e->clipPitch + c];
+    return JB_OK;
+}
+
+int jb_set_math_mode(jb_engine* e, int mode)
+{
+    if (int rc = checkEngine(e))
+        return rc;
+    if (mode < 0 || mode > 2)
+        return fail(JB_ERR_ARG, "jb_set_math_mode: mode %d (0 auto, 1 exact, 2 fast)", mode);
+    e->mathMode = mode;
     return JB_OK;
 }
 

@@ -15,1053 +15,11 @@
 // -fmad=false -ftz=true -prec-div=true -prec-sqrt=true (see Makefile).
 //
 // Reference lines are cited per routine, relative to /root/reference.
-#include "jb_device.cuh"
-
-#include <stdio.h>
+#include "jb_lane.cuh"
 
 namespace {
 
 using namespace jbdev;
-
-#define JB_CTA_THREADS 32
-#define JB_LANE_CTA_THREADS JB_CTA_THREADS
-
-// Per-sample transcendentals.  The oracle uses glibc's (nearly correctly rounded)
-// float functions; block-rate pow/log10 are evaluated in fp64 and rounded once,
-// Texture-metal's cos restates glibc's own algorithm (below), the others use
-// CUDA's <= 2 ulp float versions.
-// std::cos(float) as glibc >= 2.28 computes it (sysdeps/ieee754/flt-32/s_cosf.c + sincosf.h,
-// from ARM's optimized-routines): reduce by pi/2 in double, a degree-8 (cos) or degree-7 (sin)
-// polynomial in double, one rounding to float.  Restating the published algorithm with its
-// published coefficients makes the device bit-identical to the oracle's libm for Texture-metal's
-// per-sample pole angle, the one transcendental whose last bit the recurrences amplify
-// (SURVEY.md Appendix D.3).  glibc selects its FMA build on every x86-64 CPU with FMA, hence
-// the explicit fma() here (a double-rounding difference would be ~1e-16 relative anyway).
-__device__ __forceinline__ float cosf_glibc(float y)
-{
-    const double hpiInv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
-    const double C0 = 1.0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
-                 C4 = 0x1.99343027bf8c3p-16;
-    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
-    const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu; // abstop12
-    double x = (double) y;
-    int n = 0;
-    double sg = 1.0; // the second table row is the first with the cosine coefficients negated
-    if (top < 0x3f4u) {                 // |y| < 0.75 (abstop12(pi/4))
-        if (top < 0x398u)               // |y| < 2^-12
-            return 1.0f;
-        n = 1;
-    } else if (top < 0x42fu) {          // |y| < 120
-        const double r = x * hpiInv;
-        const int q = ((int) r + 0x800000) >> 24;
-        x = fma(-(double) q, hpi, x);
-        if (q & 2)
-            sg = -1.0;
-        if (((q + 1) & 2) != 0)         // sign[q & 3] = {1, -1, -1, 1}
-            x = -x;
-        n = q ^ 1;
-    } else {
-        return (float) cos((double) y); // outside the range any caller here produces
-    }
-    const double x2 = x * x;
-    if ((n & 1) == 0) {
-        const double x3 = x * x2;
-        const double s1 = fma(x2, S3, S2);
-        const double x7 = x3 * x2;
-        const double s = fma(x3, S1, x);
-        return (float) fma(x7, s1, s);
-    }
-    const double x4 = x2 * x2;
-    const double c2 = sg * fma(x2, C4, C3);
-    const double c1 = sg * fma(x2, C1, C0);
-    const double x6 = x4 * x2;
-    const double c = fma(x4, sg * C2, c1);
-    return (float) fma(x6, c2, c);
-}
-__device__ __forceinline__ float pow_exact(float x, float y) { return (float) pow((double) x, (double) y); }
-__device__ __forceinline__ float log10_exact(float x) { return (float) log10((double) x); }
-
-struct Lane {
-    const ProcArgs& a;
-    long long clip;
-    __device__ __forceinline__ float* sp(int var) const { return a.state + (long long) var * a.clipPitch + clip; }
-    __device__ __forceinline__ float ld(int var) const { return *sp(var); }
-    __device__ __forceinline__ void st(int var, float v) const { *sp(var) = v; }
-    __device__ __forceinline__ int ldi(int var) const { return __float_as_int(*sp(var)); }
-    __device__ __forceinline__ void sti(int var, int v) const { *sp(var) = __int_as_float(v); }
-};
-
-// ------------------------------------------------------------------ analyzer
-// JuicinessAnalyzer::analyze, src/shared/JuicinessAnalyzer.cpp:31-155.
-
-// Sums that depend only on the block's samples (not on analyzer state), shared by
-// the post-analysis of plugin s and the pre-analysis of plugin s+1 (:76-77, :86-91,
-// and getRMSLevel :105-106, which accumulates in double).
-struct BlockStats {
-    float rms = 0.0f, peak = 0.0f, side = 0.0f, corr = 0.0f;
-    double l2 = 0.0, r2 = 0.0;
-    __device__ __forceinline__ void step(float l, float r, float mono)
-    {
-        rms += mono * mono;                 // rmsAccum; midAccum is the same expression (:62, :86, :88)
-        peak = jmaxf(peak, fabsf(mono));
-        const float s = 0.5f * (l - r);
-        side += s * s;
-        corr += l * r;
-        const double dl = (double) l, dr = (double) r;
-        l2 = fma(dl, dl, l2);               // dl*dl is exact in fp64, so the fused form rounds identically
-        r2 = fma(dr, dr, r2);
-    }
-    __device__ __forceinline__ StatSums sums() const { return StatSums { rms, peak, side, corr, l2, r2 }; }
-};
-
-// One analyzer's walk over one block (jb_device.cuh: ana_step / ana_finish) with its state in the SoA arrays.
-struct AnaWalk {
-    AnaState st;
-    AnaAcc acc;
-    __device__ __forceinline__ void load(const Lane& L, int base)
-    {
-        st.sEnv = L.ld(base + AV_SHORT);
-        st.lEnv = L.ld(base + AV_LONG);
-        st.low = L.ld(base + AV_LOW);
-        st.high = L.ld(base + AV_HIGH);
-        st.cool = L.ldi(base + AV_COOLDOWN);
-    }
-    __device__ __forceinline__ void step(float mono, const AnaCoef& c) { ana_step(st, acc, mono, c); }
-    __device__ Metrics finish(const Lane& L, int base, const BlockStats& s, int n, const AnaCoef& c)
-    {
-        st.repEma = L.ld(base + AV_REP_EMA);
-        st.fatEma = L.ld(base + AV_FAT_EMA);
-        const Metrics m = ana_finish(st, acc, s.sums(), n, c);
-        L.st(base + AV_SHORT, st.sEnv);
-        L.st(base + AV_LONG, st.lEnv);
-        L.st(base + AV_LOW, st.low);
-        L.st(base + AV_HIGH, st.high);
-        L.sti(base + AV_COOLDOWN, st.cool);
-        L.st(base + AV_REP_EMA, st.repEma);
-        L.st(base + AV_FAT_EMA, st.fatEma);
-        return m;
-    }
-};
-
-// ------------------------------------------------------------------ plugin DSP ("main" part of a sweep)
-// Interface: writes() (must the sweep store samples), kSeqChannels (channel 0's whole block
-// must precede channel 1's), load/store of per-clip state, step(l, r) in place.
-
-struct MainBase {
-    __device__ __forceinline__ void quad_begin() {} // around every group of four whole samples (vector path only)
-    __device__ __forceinline__ void quad_end() {}
-    __device__ __forceinline__ float stepCh0(float l) { return l; }
-    __device__ __forceinline__ bool writes(bool outOfPlace) const { return true; }
-};
-
-struct MainNone : MainBase { // sweep 0: samples pass through untouched, nothing to publish
-    static constexpr bool kHas = false, kSeqChannels = false;
-    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
-    __device__ __forceinline__ void load(const Lane&, const SlotDesc&, int) {}
-    __device__ __forceinline__ void step(float&, float&) {}
-    __device__ __forceinline__ void store(const Lane&, const SlotDesc&) {}
-};
-
-// JuicyInfer/PluginProcessor.cpp:78-81: buffer.applyGain(trimGain) between the two analyses
-struct MainInfer : MainBase {
-    static constexpr bool kHas = true, kSeqChannels = false;
-    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
-    float g;
-    int mode;
-    __device__ __forceinline__ void load(const Lane&, const SlotDesc& d, int)
-    {
-        g = d.c.infer.trimGain;
-        mode = d.c.infer.gainMode;
-    }
-    __device__ __forceinline__ void step(float& l, float& r)
-    {
-        if (mode == 1) {
-            l *= g;
-            r *= g;
-        } else if (mode == 2) {
-            l = 0.0f;
-            r = 0.0f;
-        }
-    }
-    __device__ __forceinline__ void store(const Lane&, const SlotDesc&) {}
-    __device__ __forceinline__ bool writes(bool outOfPlace) const { return mode != 0 || outOfPlace; }
-};
-
-// JuicySaturator/PluginProcessor.cpp:83-98
-struct MainSat : MainBase {
-    static constexpr bool kHas = true, kSeqChannels = false;
-    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
-    float s0, s1;
-    SatCoef c;
-    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
-    {
-        c = d.c.sat;
-        const int b = d.stateBase + AV_COUNT;
-        s0 = L.ld(b + SV_TONE0);
-        s1 = L.ld(b + SV_TONE1);
-    }
-    __device__ __forceinline__ float one(float dry, float& state) const
-    {
-        const float driven = dry * c.inGain;
-        const float skewed = driven + c.asym * driven * driven;
-        const float soft = tanh_fast(skewed); // MUFU-based, <= 1e-7 absolute (jb_device.cuh)
-        state += c.toneCoeff * (soft - state);
-        const float wet = state * c.outGain;
-        return dry + c.mix * (wet - dry);
-    }
-    __device__ __forceinline__ void step(float& l, float& r)
-    {
-        l = one(l, s0);
-        r = one(r, s1);
-    }
-    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
-    {
-        const int b = d.stateBase + AV_COUNT;
-        L.st(b + SV_TONE0, s0);
-        L.st(b + SV_TONE1, s1);
-    }
-};
-
-// JuicyPunch/PluginProcessor.cpp:86-112
-struct MainPunch : MainBase {
-    static constexpr bool kHas = true, kSeqChannels = false;
-    static constexpr bool kHeavy = true; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
-    float f0, f1, sl0, sl1, invTanhDrive;
-    PunchCoef c;
-    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
-    {
-        c = d.c.punch;
-        invTanhDrive = 1.0f / c.tanhDrive;
-        const int b = d.stateBase + AV_COUNT;
-        f0 = L.ld(b + PV_FAST0);
-        f1 = L.ld(b + PV_FAST1);
-        sl0 = L.ld(b + PV_SLOW0);
-        sl1 = L.ld(b + PV_SLOW1);
-    }
-    __device__ __forceinline__ float one(float dry, float& fEnv, float& sEnv) const
-    {
-        const float adry = fabsf(dry);
-        fEnv = c.omFast * adry + c.fastCoeff * fEnv;
-        sEnv = c.omSlow * adry + c.slowCoeff * sEnv;
-        const float transient = jmaxf(0.0f, fEnv - sEnv);
-        const float transientCurve = pow_unit(transient, c.curveExp); // MUFU-based (jb_device.cuh), like the cooperative kernel
-        const float punchGain = 1.0f + c.punchK * transientCurve;
-        const float sustainGain = 1.0f + c.sustainK * jmaxf(0.0f, sEnv - transient * 0.6f);
-        float wet = dry * punchGain * sustainGain;
-        const float soft = tanh_fast(wet * c.drive) * invTanhDrive;
-        const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
-        wet = soft + c.clipAmt * (hard - soft);
-        return (dry + c.mix * (wet - dry)) * c.outGain;
-    }
-    __device__ __forceinline__ void step(float& l, float& r)
-    {
-        l = one(l, f0, sl0);
-        r = one(r, f1, sl1);
-    }
-    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
-    {
-        const int b = d.stateBase + AV_COUNT;
-        L.st(b + PV_FAST0, f0);
-        L.st(b + PV_FAST1, f1);
-        L.st(b + PV_SLOW0, sl0);
-        L.st(b + PV_SLOW1, sl1);
-    }
-};
-
-// JuicyWidth/PluginProcessor.cpp:91-137.  The delay line keeps only the right
-// channel's wet signal (the left ring is written but never read, :122,:131).
-// Ring layouts: clip-major [clip][ringLen] (pitch 1; what the engine uses) or time-major
-// [ringLen][clip].  With the clip-major ring and everything a multiple of four samples (ring
-// length, delay, write position: the usual 2880 / 576 case) a quad of wet samples is stored with
-// one 16-byte store and the delayed quad is fetched with one 16-byte load issued a quad EARLY --
-// the delayed samples were written delaySamples ago -- so the ring's L2 / HBM latency no longer
-// sits in front of every sample (it was 55 % of all stall samples, profiles/r01_width_lane_*).
-struct MainWidth : MainBase {
-    static constexpr bool kHas = true, kSeqChannels = false;
-    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
-    float width;
-    int wpos;
-    WidthCoef c;
-    float* ring;
-    long long pitch;
-    bool quads;          // vector ring path
-    static constexpr int kDepth = 1; // quads fetched ahead of use (needs delay >= 4 * kDepth + 4)
-    float4 ahead[kDepth]; // delayed quads of the next kDepth quad_begin calls
-    float d0, d1, d2, d3; // delayed samples of the current quad, next first
-    float w0, w1, w2, w3; // wet samples of the current quad, oldest first (static shifts keep both in registers)
-    __device__ __forceinline__ int delayed_pos(int p) const
-    {
-        int rp = p - c.delaySamples;
-        if (rp < 0)
-            rp += c.ringLen;
-        return rp;
-    }
-    __device__ __forceinline__ int wrap(int p) const { return p >= c.ringLen ? p - c.ringLen : p; }
-    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
-    {
-        c = d.c.width;
-        width = c.width; // re-read from the parameter every block (:93)
-        wpos = L.ldi(d.stateBase + AV_COUNT + WV_WPOS);
-        ring = L.a.widthRing + L.clip * L.a.ringClipStride;
-        pitch = L.a.ringTimeStride;
-        quads = L.a.vecOk != 0 && pitch == 1 && ((c.ringLen | c.delaySamples | wpos | (int) L.a.ringClipStride) & 3) == 0
-                && c.delaySamples >= 4 * kDepth + 4 && c.ringLen >= 8 * kDepth + 8;
-        d0 = d1 = d2 = d3 = w0 = w1 = w2 = w3 = 0.0f;
-        if (quads) {
-#pragma unroll
-            for (int j = 0; j < kDepth; ++j)
-                ahead[j] = *reinterpret_cast<const float4*>(ring + delayed_pos(wrap(wpos + 4 * j)));
-        }
-    }
-    __device__ __forceinline__ void quad_begin()
-    {
-        if (!quads)
-            return;
-        d0 = ahead[0].x; d1 = ahead[0].y; d2 = ahead[0].z; d3 = ahead[0].w;
-#pragma unroll
-        for (int j = 0; j + 1 < kDepth; ++j)
-            ahead[j] = ahead[j + 1];
-        // the quad used kDepth calls from now was written >= 4 samples ago (delay >= 4 kDepth + 4)
-        ahead[kDepth - 1] = *reinterpret_cast<const float4*>(ring + delayed_pos(wrap(wpos + 4 * kDepth)));
-    }
-    __device__ __forceinline__ void quad_end()
-    {
-        if (!quads)
-            return;
-        *reinterpret_cast<float4*>(ring + wpos) = make_float4(w0, w1, w2, w3);
-        wpos += 4;
-        if (wpos >= c.ringLen)
-            wpos = 0;
-    }
-    __device__ __forceinline__ void step(float& l, float& r)
-    {
-        const float dryL = l, dryR = r;
-        const float corrProxy = jlimitf(-1.0f, 1.0f, dryL * dryR * 12.0f);
-        if (corrProxy < -0.1f)
-            width *= c.dynamicLimit;
-        const float mid = 0.5f * (dryL + dryR);
-        const float side = 0.5f * (dryL - dryR) * (1.0f + width);
-        const float wetL = mid + side;
-        float wetR = mid - side;
-        if (quads) {
-            w0 = w1; w1 = w2; w2 = w3; w3 = wetR;
-            wetR = d0;
-            d0 = d1; d1 = d2; d2 = d3;
-        } else {
-            ring[(long long) wpos * pitch] = wetR;
-            wetR = ring[(long long) delayed_pos(wpos) * pitch];
-            if (++wpos >= c.ringLen)
-                wpos = 0;
-        }
-        l = (dryL + c.mix * (wetL - dryL)) * c.outGain;
-        r = (dryR + c.mix * (wetR - dryR)) * c.outGain;
-    }
-    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d) { L.sti(d.stateBase + AV_COUNT + WV_WPOS, wpos); }
-};
-
-// JuicyCohere/PluginProcessor.cpp:99-119 (lpA/lpB restart at 0 every block, :103-104)
-struct MainCohere : MainBase {
-    static constexpr bool kHas = true, kSeqChannels = false;
-    static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
-    float t0, t1, a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
-    float lowComp, midComp, highComp;
-    CohereCoef c;
-    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
-    {
-        c = d.c.cohere;
-        const int b = d.stateBase + AV_COUNT;
-        t0 = L.ld(b + CV_TAIL0);
-        t1 = L.ld(b + CV_TAIL1);
-        lowComp = L.ld(b + CV_COMP_LOW);
-        midComp = L.ld(b + CV_COMP_MID);
-        highComp = L.ld(b + CV_COMP_HIGH);
-    }
-    __device__ __forceinline__ float one(float dry, float& lpA, float& lpB, float& tail) const
-    {
-        lpA += c.lowCoeff * (dry - lpA);
-        lpB += c.highCoeff * (dry - lpB);
-        const float low = lpA * lowComp;
-        const float high = (dry - lpB) * highComp;
-        const float mid = (dry - lpA - (dry - lpB)) * midComp;
-        const float matched = low + mid + high;
-        tail = matched + tail * c.fb;
-        const float wet = matched + c.tailK * tail;
-        return (dry + c.mix * (wet - dry)) * c.outGain;
-    }
-    __device__ __forceinline__ void step(float& l, float& r)
-    {
-        l = one(l, a0, b0, t0);
-        r = one(r, a1, b1, t1);
-    }
-    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
-    {
-        const int b = d.stateBase + AV_COUNT;
-        L.st(b + CV_TAIL0, t0);
-        L.st(b + CV_TAIL1, t1);
-    }
-};
-
-// JuicyTexture ChannelState (JuicyTexture/PluginProcessor.h:55-77) held in registers
-struct TexChan {
-    float tail, lp, hp, env, wetEnv, noiseHp, dcIn, dcOut, protectGain, springPos, springVel;
-    float fleshPosA, fleshVelA, fleshPosB, fleshVelB, prevWave;
-    float y1[4], y2[4];
-    __device__ __forceinline__ void load(const Lane& L, int b)
-    {
-        tail = L.ld(b + TV_TAIL); lp = L.ld(b + TV_LP); hp = L.ld(b + TV_HP); env = L.ld(b + TV_ENV);
-        wetEnv = L.ld(b + TV_WETENV); noiseHp = L.ld(b + TV_NOISEHP); dcIn = L.ld(b + TV_DCIN); dcOut = L.ld(b + TV_DCOUT);
-        protectGain = L.ld(b + TV_PROTECT); springPos = L.ld(b + TV_SPRING_POS); springVel = L.ld(b + TV_SPRING_VEL);
-        fleshPosA = L.ld(b + TV_FLESH_PA); fleshVelA = L.ld(b + TV_FLESH_VA); fleshPosB = L.ld(b + TV_FLESH_PB);
-        fleshVelB = L.ld(b + TV_FLESH_VB); prevWave = L.ld(b + TV_PREVWAVE);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            y1[k] = L.ld(b + TV_Y1_0 + k);
-            y2[k] = L.ld(b + TV_Y2_0 + k);
-        }
-    }
-    __device__ __forceinline__ void store(const Lane& L, int b) const
-    {
-        L.st(b + TV_TAIL, tail); L.st(b + TV_LP, lp); L.st(b + TV_HP, hp); L.st(b + TV_ENV, env);
-        L.st(b + TV_WETENV, wetEnv); L.st(b + TV_NOISEHP, noiseHp); L.st(b + TV_DCIN, dcIn); L.st(b + TV_DCOUT, dcOut);
-        L.st(b + TV_PROTECT, protectGain); L.st(b + TV_SPRING_POS, springPos); L.st(b + TV_SPRING_VEL, springVel);
-        L.st(b + TV_FLESH_PA, fleshPosA); L.st(b + TV_FLESH_VA, fleshVelA); L.st(b + TV_FLESH_PB, fleshPosB);
-        L.st(b + TV_FLESH_VB, fleshVelB); L.st(b + TV_PREVWAVE, prevWave);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            L.st(b + TV_Y1_0 + k, y1[k]);
-            L.st(b + TV_Y2_0 + k, y2[k]);
-        }
-    }
-};
-
-// JuicyTexture/PluginProcessor.cpp:107-278, one material per instantiation.
-// The LCG `rng` is one instance member advanced by channel 0's whole block and
-// then by channel 1's (:107,:114,:239); channel 1 therefore starts n draws ahead
-// (affine skip-ahead), which lets both channels run sample-interleaved.
-template <int MAT>
-struct MainTexture : MainBase {
-    static constexpr bool kHas = true, kSeqChannels = false;
-    static constexpr bool kHeavy = true; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
-    TexChan ch0, ch1;
-    uint32_t rng0, rng1;
-    int waveIdx;
-    const TexCoef* c;
-    float* wave;
-    long long pitch;
-
-    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int n)
-    {
-        c = &d.c.tex;
-        const int b = d.stateBase + AV_COUNT;
-        ch0.load(L, b);
-        ch1.load(L, b + TV_CH_STRIDE);
-        waveIdx = L.ldi(b + TV_WAVEIDX);
-        rng0 = (uint32_t) L.ldi(b + TV_RNG);
-        uint32_t A = 1664525u, C = 1013904223u, accA = 1u, accC = 0u; // x -> A^n x + C_n
-        for (int k = n; k > 0; k >>= 1) {
-            if (k & 1) {
-                accA *= A;
-                accC = accC * A + C;
-            }
-            C = (A + 1u) * C;
-            A *= A;
-        }
-        rng1 = accA * rng0 + accC;
-        wave = L.a.texWave + L.clip;
-        pitch = L.a.clipPitch;
-    }
-
-    // modeStep with block-constant pole radius (:77-89); a1 is passed in
-    __device__ __forceinline__ float mode(TexChan& st, int k, float exc, float a1) const
-    {
-        const float y = exc * c->modeGain[k] + a1 * st.y1[k] + c->modeA2[k] * st.y2[k];
-        st.y2[k] = st.y1[k];
-        st.y1[k] = y;
-        return y;
-    }
-    __device__ __forceinline__ float metalA1(int k, float bend) const
-    {
-        const float f = jlimitf(20.0f, c->fMax, c->modeF[k] * bend);
-        const float theta = 2.0f * PI_F * f / c->srf;
-        return c->modeTwoR[k] * cosf_glibc(theta);
-    }
-    // waveguideRead (:91-105) on the time-major ring of this channel
-    __device__ __forceinline__ float waveRead(const float* line) const
-    {
-        const int size = c->waveSize;
-        float pos = (float) waveIdx - c->delaySamp;
-        while (pos < 0.0f)
-            pos += (float) size;
-        while (pos >= (float) size)
-            pos -= (float) size;
-        const int i0 = (int) pos;
-        const int i1 = (i0 + 1) % size;
-        const float frac = pos - (float) i0;
-        return jmap3(frac, line[(long long) i0 * pitch], line[(long long) i1 * pitch]);
-    }
-
-    __device__ __forceinline__ float one(float dry, TexChan& st, uint32_t& rng, float* line) const
-    {
-        const TexCoef& k = *c;
-        const float driven = dry * k.inTrim;
-        const float adry = fabsf(dry);
-        {
-            const bool up = adry > st.env;
-            st.env = (up ? k.envAtk : k.envRel) * st.env + (up ? k.omEnvAtk : k.omEnvRel) * adry;
-        }
-        const float impact = jlimitf(0.0f, 1.0f, jmaxf(0.0f, adry - st.env) * 10.0f);
-        const float body = jlimitf(0.0f, 1.0f, st.env * 3.2f);
-        const float trail = jlimitf(0.0f, 1.0f, 1.0f - impact) * k.tailShape;
-
-        st.lp += k.splitLow * (driven - st.lp);
-        st.hp += k.splitHigh * (driven - st.hp);
-        const float low = st.lp * k.lowBoost;
-        const float high = (driven - st.hp);
-        const float mid = driven - st.lp - high;
-        const float core = low + mid + high * k.highTilt;
-
-        float shaped;
-        if (MAT == 0) { // gel :137-151
-            const float zeta = jmap3(trail, 0.62f, 1.45f);
-            const float cc = 2.0f * zeta * k.gelOmega;
-            const float force = core * (0.52f + 0.62f * body);
-            const float acc = k.gelK * (force - st.springPos) - cc * st.springVel;
-            st.springVel += acc;
-            st.springPos += st.springVel;
-            shaped = 0.48f * core + 1.85f * st.springPos;
-            shaped = tanhf(shaped * k.shapeGain);
-        } else if (MAT == 1) { // metal :152-169
-            const float exc = core * (0.19f + 0.52f * impact);
-            const float bend = 1.0f + 0.09f * impact;
-            const float m0 = mode(st, 0, exc, metalA1(0, bend));
-            const float m1 = mode(st, 1, exc, metalA1(1, bend));
-            const float m2 = mode(st, 2, exc, metalA1(2, bend));
-            const float m3 = mode(st, 3, exc, metalA1(3, bend));
-            const float modes = m0 + m1 + m2 + m3;
-            const float brightExcite = 0.03f * impact * (core - st.hp);
-            shaped = (0.44f * core + 0.42f * modes + brightExcite) * k.shapeGain;
-        } else if (MAT == 2 || MAT == 3) { // wood :170-192, plastic :193-213
-            const float exc = core * (k.excA + k.excB * impact);
-            const float delayed = waveRead(line);
-            float newWave;
-            if (MAT == 2)
-                newWave = k.waveDamp * (0.62f * delayed + 0.38f * st.prevWave) + exc * (0.09f + 0.04f * body);
-            else
-                newWave = k.waveDamp * (0.76f * delayed + 0.24f * st.prevWave) + 0.14f * exc;
-            line[(long long) waveIdx * pitch] = newWave;
-            st.prevWave = delayed;
-            const float w0 = mode(st, 0, exc, k.modeA1[0]);
-            const float w1 = mode(st, 1, exc, k.modeA1[1]);
-            const float w2 = mode(st, 2, exc, k.modeA1[2]);
-            const float w3 = mode(st, 3, exc, k.modeA1[3]);
-            shaped = (k.waveMixA * core + k.waveMixB * delayed + k.waveOut * (w0 + w1 + w2 + w3)) * k.shapeGain;
-        } else { // flesh :214-236
-            const float force = core * (0.55f + 0.65f * body);
-            const float accA = k.kA * (force - st.fleshPosA) - k.cA * st.fleshVelA - k.kCouple * (st.fleshPosA - st.fleshPosB);
-            const float accB = k.kB * (st.fleshPosA - st.fleshPosB) - k.cB * st.fleshVelB;
-            st.fleshVelA += accA;
-            st.fleshVelB += accB;
-            st.fleshPosA += st.fleshVelA;
-            st.fleshPosB += st.fleshVelB;
-            const float tissue = 0.92f * st.fleshPosA + 0.58f * st.fleshPosB;
-            const float nl = tissue - 0.19f * tissue * tissue * tissue;
-            shaped = tanhf((0.50f * core + 1.34f * nl) * k.shapeGain);
-        }
-
-        rng = 1664525u * rng + 1013904223u; // :239-243
-        const float white = ((float) ((rng >> 8) & 0xFFFFu) / 32768.0f - 1.0f);
-        st.noiseHp += 0.08f * (white - st.noiseHp);
-        const float rough = white - st.noiseHp;
-        shaped += rough * k.noiseAmt * (0.14f + 0.64f * impact);
-
-        const float dynamics = 1.0f + impact * k.dynK + body * 0.06f;
-        shaped *= dynamics * k.matTrim;
-
-        const float tailInput = jlimitf(-2.0f, 2.0f, shaped) * (0.45f + 0.55f * trail);
-        st.tail = tailInput + st.tail * k.decay;
-        float wet = shaped + st.tail * (0.30f + 0.45f * trail);
-
-        const float wetAbs = fabsf(wet); // :253-257
-        {
-            const bool up = wetAbs > st.wetEnv;
-            st.wetEnv = (up ? k.wetAtk : k.wetRel) * st.wetEnv + (up ? k.omWetAtk : k.omWetRel) * wetAbs;
-        }
-        const float autoComp = k.autoGainBase / (1.0f + 1.8f * st.wetEnv);
-        wet *= jlimitf(0.18f, 1.0f, autoComp);
-
-        const float mixed = dry + k.mix * (wet - dry);
-        float out = mixed * k.outGain;
-
-        const float dcBlocked = out - st.dcIn + 0.995f * st.dcOut; // :263-265
-        st.dcIn = out;
-        st.dcOut = dcBlocked;
-
-        const float peak = fabsf(dcBlocked); // :268-276
-        if (peak > 0.88f)
-            st.protectGain = jminf(st.protectGain, (0.88f / peak) * 0.98f);
-        else
-            st.protectGain += (1.0f - st.protectGain) * 0.0028f;
-        out = dcBlocked * jlimitf(0.2f, 1.0f, st.protectGain);
-        return jlimitf(-0.98f, 0.98f, out);
-    }
-
-    __device__ __forceinline__ void step(float& l, float& r)
-    {
-        float* line0 = wave;
-        float* line1 = wave + (long long) c->waveSize * pitch;
-        l = one(l, ch0, rng0, line0);
-        r = one(r, ch1, rng1, line1);
-        if (MAT == 2 || MAT == 3)
-            waveIdx = (waveIdx + 1) % c->waveSize;
-    }
-    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
-    {
-        const int b = d.stateBase + AV_COUNT;
-        ch0.store(L, b);
-        ch1.store(L, b + TV_CH_STRIDE);
-        L.sti(b + TV_WAVEIDX, waveIdx);
-        L.sti(b + TV_RNG, (int) rng1); // state after both channels' draws
-    }
-};
-
-// JuicyMotion/PluginProcessor.cpp:101-142.  variation*, motionPhase and budgetEnv
-// are instance members walked by channel 0's whole block and then channel 1's, so
-// the main part runs as two sequential channel passes (kSeqChannels).
-struct MainMotion : MainBase {
-    static constexpr bool kHas = true, kSeqChannels = true;
-    static constexpr bool kHeavy = true; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
-    float vTone, vTrans, vTail, tTone, tTrans, tTail, phase, budget;
-    float tail0, tail1, lp0, lp1, prev0, prev1, repScale, recovery;
-    MotionCoef c;
-    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
-    {
-        c = d.c.motion;
-        const int b = d.stateBase + AV_COUNT;
-        vTone = L.ld(b + MV_VTONE); vTrans = L.ld(b + MV_VTRANS); vTail = L.ld(b + MV_VTAIL);
-        tTone = L.ld(b + MV_TTONE); tTrans = L.ld(b + MV_TTRANS); tTail = L.ld(b + MV_TTAIL);
-        phase = L.ld(b + MV_PHASE); budget = L.ld(b + MV_BUDGET);
-        tail0 = L.ld(b + MV_TAIL0); tail1 = L.ld(b + MV_TAIL1);
-        lp0 = L.ld(b + MV_LP0); lp1 = L.ld(b + MV_LP1);
-        prev0 = L.ld(b + MV_PREV0); prev1 = L.ld(b + MV_PREV1);
-        repScale = L.ld(b + MV_REP_SCALE); recovery = L.ld(b + MV_RECOVERY);
-    }
-    __device__ __forceinline__ float one(float dry, float lfoOffset, float& tail, float& lp, float& prev)
-    {
-        vTone = c.varSlew * vTone + c.omVarSlew * tTone;
-        vTrans = c.varSlew * vTrans + c.omVarSlew * tTrans;
-        vTail = c.varSlew * vTail + c.omVarSlew * tTail;
-        phase += c.motionInc;
-        if (phase > 2.0f * PI_F)
-            phase -= 2.0f * TWO_PI_F; // sic (:114-115)
-
-        const float motionLfo = sinf(phase + lfoOffset);
-        const float cutoff = jlimitf(120.0f, 4200.0f, 900.0f + vTone * 1100.0f * c.d06 + motionLfo * c.lfoDepth);
-        const float lpCoeff = 1.0f - expf(-2.0f * PI_F * cutoff / c.srf);
-        lp += lpCoeff * (dry - lp);
-        const float hp = dry - lp;
-        const float transient = dry - prev;
-        prev = dry;
-
-        const float transientBoost = 1.0f + vTrans * 1.2f * c.d07 + c.mv035 * motionLfo * c.d08;
-        const float toneShift = lp * (1.0f + vTone * 0.65f * c.d0507) + hp * transientBoost + transient * c.mvT * c.d0508;
-        tail = toneShift + tail * jlimitf(0.0f, 0.93f, c.tailFeedback + vTail * 0.06f);
-
-        float wet = toneShift * repScale * recovery + c.tailMix * tail;
-        budget = c.budgetCoeff * budget + c.omBudget * fabsf(wet);
-        const float limiterGain = budget > c.budgetTarget ? c.budgetTarget / (budget + 1.0e-5f) : 1.0f;
-        wet *= limiterGain;
-        return (dry + c.mix * (wet * c.wetBoost - dry)) * c.outGain;
-    }
-    __device__ __forceinline__ float stepCh0(float l) { return one(l, 0.0f, tail0, lp0, prev0); }
-    __device__ __forceinline__ void step(float&, float& r) { r = one(r, 0.85f, tail1, lp1, prev1); }
-    __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
-    {
-        const int b = d.stateBase + AV_COUNT;
-        L.st(b + MV_VTONE, vTone); L.st(b + MV_VTRANS, vTrans); L.st(b + MV_VTAIL, vTail);
-        L.st(b + MV_PHASE, phase); L.st(b + MV_BUDGET, budget);
-        L.st(b + MV_TAIL0, tail0); L.st(b + MV_TAIL1, tail1);
-        L.st(b + MV_LP0, lp0); L.st(b + MV_LP1, lp1);
-        L.st(b + MV_PREV0, prev0); L.st(b + MV_PREV1, prev1);
-    }
-};
-
-// ------------------------------------------------------------------ block pre-passes of the NEXT plugin
-
-struct PreNone { // no next plugin
-    static constexpr bool kHas = false;
-    __device__ __forceinline__ void load(const Lane&, const SlotDesc&) {}
-    __device__ __forceinline__ void step(float, float, float) {}
-    __device__ __forceinline__ void finish(const Lane&, const SlotDesc&, int) {}
-};
-struct PreAna { // next plugin needs only its analyzer's pre pass
-    static constexpr bool kHas = true;
-    __device__ __forceinline__ void load(const Lane&, const SlotDesc&) {}
-    __device__ __forceinline__ void step(float, float, float) {}
-    __device__ __forceinline__ void finish(const Lane&, const SlotDesc&, int) {}
-};
-
-// JuicyCohere/PluginProcessor.cpp:62-96: band energies of the block's mono sum through
-// the persistent 220/2400 Hz one-poles, optional target learning, context fit and
-// the three compensation gains used by the main loop.
-struct PreCohere {
-    static constexpr bool kHas = true;
-    float lowLp, highLp, eLow = 0.0f, eMid = 0.0f, eHigh = 0.0f;
-    CohereCoef c;
-    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d)
-    {
-        c = d.c.cohere;
-        const int b = d.stateBase + AV_COUNT;
-        lowLp = L.ld(b + CV_LOWLP);
-        highLp = L.ld(b + CV_HIGHLP);
-    }
-    __device__ __forceinline__ void step(float, float, float mono)
-    {
-        lowLp += c.lowCoeff * (mono - lowLp);
-        highLp += c.highCoeff * (mono - highLp);
-        const float low = lowLp;
-        const float high = mono - highLp;
-        const float mid = mono - low - high;
-        eLow += low * low;
-        eMid += mid * mid;
-        eHigh += high * high;
-    }
-    static __device__ __forceinline__ float gainToDb(float g) { return g > 0.0f ? jmaxf(-100.0f, log10_exact(g) * 20.0f) : -100.0f; }
-    __device__ void finish(const Lane& L, const SlotDesc& d, int n)
-    {
-        const int b = d.stateBase + AV_COUNT;
-        const float inv = 1.0f / (float) (n > 1 ? n : 1);
-        eLow *= inv;
-        eMid *= inv;
-        eHigh *= inv;
-        float tLow = L.ld(b + CV_TGT_LOW), tMid = L.ld(b + CV_TGT_MID), tHigh = L.ld(b + CV_TGT_HIGH);
-        if (c.learn) {
-            tLow += (eLow - tLow) * 0.02f;
-            tMid += (eMid - tMid) * 0.02f;
-            tHigh += (eHigh - tHigh) * 0.02f;
-            L.st(b + CV_TGT_LOW, tLow);
-            L.st(b + CV_TGT_MID, tMid);
-            L.st(b + CV_TGT_HIGH, tHigh);
-        }
-        const float lowErr = fabsf(gainToDb((eLow + 1.0e-6f) / (tLow + 1.0e-6f)));
-        const float midErr = fabsf(gainToDb((eMid + 1.0e-6f) / (tMid + 1.0e-6f)));
-        const float highErr = fabsf(gainToDb((eHigh + 1.0e-6f) / (tHigh + 1.0e-6f)));
-        const float deviation = (lowErr + midErr + highErr) / 3.0f;
-        const float contextFit = jlimitf(0.0f, 100.0f, 100.0f - deviation * 10.0f);
-        L.st(b + CV_FIT, output_param(contextFit, 0.0f, 100.0f));
-        L.st(b + CV_COMP_LOW, jlimitf(0.5f, 1.8f, pow_exact((tLow + 1.0e-6f) / (eLow + 1.0e-6f), c.matchQ)));
-        L.st(b + CV_COMP_MID, jlimitf(0.5f, 1.8f, pow_exact((tMid + 1.0e-6f) / (eMid + 1.0e-6f), c.matchQ)));
-        L.st(b + CV_COMP_HIGH, jlimitf(0.5f, 1.8f, pow_exact((tHigh + 1.0e-6f) / (eHigh + 1.0e-6f), c.matchQ)));
-        L.st(b + CV_LOWLP, lowLp);
-        L.st(b + CV_HIGHLP, highLp);
-    }
-};
-
-// JuicyMotion/PluginProcessor.cpp:75-99: onset detector over the block's mono sum,
-// LCG-drawn variation targets, repetition counter and the two block scalars.
-struct PreMotion {
-    static constexpr bool kHas = true;
-    float env, repetition, tTone, tTrans, tTail;
-    int cool;
-    uint32_t rng;
-    MotionCoef c;
-    __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d)
-    {
-        c = d.c.motion;
-        const int b = d.stateBase + AV_COUNT;
-        env = L.ld(b + MV_ENV);
-        repetition = L.ld(b + MV_REPETITION);
-        tTone = L.ld(b + MV_TTONE);
-        tTrans = L.ld(b + MV_TTRANS);
-        tTail = L.ld(b + MV_TTAIL);
-        cool = L.ldi(b + MV_COOLDOWN);
-        rng = (uint32_t) L.ldi(b + MV_RNG);
-    }
-    __device__ __forceinline__ void step(float, float, float mono)
-    {
-        const float absMono = fabsf(mono);
-        env = c.envCoeff * env + c.omEnv * absMono;
-        if (cool > 0)
-            --cool;
-        if (absMono > env * 1.35f + 0.02f && cool <= 0) {
-            cool = c.cooldownLen;
-            repetition += 1.0f;
-            rng = 1664525u * rng + 1013904223u;
-            tTone = (((float) ((rng >> 7) & 0x7FFFu) / 16384.0f) - 1.0f) * c.microVar * 0.9f;
-            rng = 1664525u * rng + 1013904223u;
-            tTrans = (((float) ((rng >> 9) & 0x7FFFu) / 16384.0f) - 1.0f) * c.microVar * 0.8f;
-            rng = 1664525u * rng + 1013904223u;
-            tTail = (((float) ((rng >> 11) & 0x7FFFu) / 16384.0f) - 1.0f) * c.microVar * 0.8f;
-        }
-        repetition *= 0.997f;
-    }
-    __device__ void finish(const Lane& L, const SlotDesc& d, int)
-    {
-        const int b = d.stateBase + AV_COUNT;
-        const float repNorm = jlimitf(0.0f, 1.0f, repetition * 0.08f);
-        L.st(b + MV_REP_SCALE, 1.0f - c.repeatCtrl * repNorm * 0.65f);
-        L.st(b + MV_RECOVERY, 1.0f + c.repeatCtrl * (1.0f - repNorm) * 0.25f);
-        L.st(b + MV_ENV, env);
-        L.st(b + MV_REPETITION, repetition);
-        L.st(b + MV_TTONE, tTone);
-        L.st(b + MV_TTRANS, tTrans);
-        L.st(b + MV_TTAIL, tTail);
-        L.sti(b + MV_COOLDOWN, cool);
-        L.sti(b + MV_RNG, (int) rng);
-    }
-};
-
-// ------------------------------------------------------------------ sample access (v1: per-lane row streaming)
-
-struct Quad { float v[4]; };
-
-__device__ __forceinline__ Quad load4(const float* p, int i, int n, bool vec)
-{
-    Quad q;
-    if (vec && i + 4 <= n) {
-        const float4 t = *reinterpret_cast<const float4*>(p + i);
-        q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            q.v[k] = (i + k < n) ? p[i + k] : 0.0f;
-    }
-    return q;
-}
-__device__ __forceinline__ void store4(float* p, int i, int n, bool vec, const Quad& q)
-{
-    if (vec && i + 4 <= n) {
-        *reinterpret_cast<float4*>(p + i) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (i + k < n)
-                p[i + k] = q.v[k];
-    }
-}
-
-// ---- sample access (v2): lane-local asynchronous prefetch ring.
-// A lane streams its own two rows, so a warp's loads are 32 separate 16-byte pieces and their L2 /
-// HBM latency (hundreds of cycles) used to sit in front of every four samples.  Each lane now copies
-// its rows with cp.async (no register landing, no scoreboard wait) into a private 2 x 32-sample ring
-// in shared memory 24 samples ahead of use and reads them back one quad ahead.  Piece k of a row is
-// stored at k ^ (lane & 7) so that the 8 lanes of a quarter-warp hit 8 different bank groups.
-constexpr int LF_AHEAD = 6; // quads in flight per row (ring: 8 quads = 128 B per row, 8 KB per warp: 16+ warps per SM stay resident)
-
-__device__ __forceinline__ uint32_t lf_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-// CACHE_L1: the 32-byte sector a piece belongs to is kept in L1, so the row's next piece does not go to L2 again
-// (big light batches, where L2 sector throughput is the bound); otherwise the copies bypass L1.
-template <bool CACHE_L1>
-__device__ __forceinline__ void lf_cp_async16(uint32_t dst, const void* src)
-{
-    if (CACHE_L1)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    else
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void lf_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void lf_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ Quad lf_lds(uint32_t addr)
-{
-    Quad q;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]) : "r"(addr) : "memory");
-    return q;
-}
-struct LaneFeed {
-    uint32_t base;           // shared address of this lane's 256-byte ring (row L, then row R), swizzle folded in
-    const float *srcL, *srcR;
-    int nQuads;
-    __device__ __forceinline__ void init(const float* l, const float* r, int n)
-    {
-        __shared__ __align__(256) float4 ring[JB_LANE_CTA_THREADS * 16];
-        base = lf_smem_u32(&ring[threadIdx.x * 16]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
-        asm volatile("" : "+r"(base));
-        srcL = l;
-        srcR = r;
-        nQuads = n >> 2;
-    }
-    template <bool CACHE_L1>
-    __device__ __forceinline__ void issue(int q) const // quad q of both rows -> ring piece q & 7; always commits a group
-    {
-        if (q < nQuads) {
-            const uint32_t off = (uint32_t) (q & 7) << 4;
-            lf_cp_async16<CACHE_L1>(base ^ off, srcL + 4 * q);
-            lf_cp_async16<CACHE_L1>((base ^ off) + 128u, srcR + 4 * q);
-        }
-        lf_commit();
-    }
-    __device__ __forceinline__ void read(int q, Quad& l, Quad& r) const
-    {
-        const uint32_t off = (uint32_t) (q & 7) << 4;
-        l = lf_lds(base ^ off);
-        r = lf_lds((base ^ off) + 128u);
-    }
-};
-
-// Eight samples = one 32-byte sector per store (STG.256, sm_100): half the L2 write requests of two 16-byte stores.
-__device__ __forceinline__ void store8(float* p, const Quad& a, const Quad& b)
-{
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.v[0]), "f"(a.v[1]), "f"(a.v[2]), "f"(a.v[3]),
-                 "f"(b.v[0]), "f"(b.v[1]), "f"(b.v[2]), "f"(b.v[3])
-                 : "memory");
-}
-
-// One sweep over one block of one clip.  mainSlot < 0 for sweep 0.
-template <class Main, class Pre>
-__device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
-{
-    const Lane L { a, clip };
-    const int preSlot = mainSlot + 1;
-    const bool firstRead = mainSlot <= 0; // sweep 0 and plugin 0's sweep read the caller's input
-    const long long rowL = (clip * a.nCh) * a.rowPitch + pos;
-    const long long rowR = rowL + a.rowPitch;
-    const float* srcL = (firstRead ? a.in : a.out) + rowL;
-    const float* srcR = (firstRead ? a.in : a.out) + rowR;
-    float* dstL = a.out + rowL;
-    float* dstR = a.out + rowR;
-    const bool vec = a.vecOk != 0;
-
-    Main mainPart;
-    AnaWalk post, pre;
-    Pre prePart;
-    BlockStats stats;
-    const AnaCoef ana = a.ana;
-    bool mustWrite = false;
-    if constexpr (Main::kHas) {
-        mainPart.load(L, a.slot[mainSlot], n);
-        post.load(L, a.slot[mainSlot].stateBase);
-        mustWrite = mainPart.writes(a.in != a.out);
-    }
-    if constexpr (Pre::kHas) {
-        pre.load(L, a.slot[preSlot].stateBase);
-        prePart.load(L, a.slot[preSlot]);
-    }
-
-    if constexpr (Main::kSeqChannels) { // Motion: channel 0's block first
-        for (int i = 0; i < n; i += 4) {
-            Quad q = load4(srcL, i, n, vec);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (i + k < n)
-                    q.v[k] = mainPart.stepCh0(q.v[k]);
-            store4(dstL, i, n, vec, q);
-        }
-        srcL = dstL;
-    }
-
-    auto quad_math = [&](Quad& ql, Quad& qr, int i) {
-        if (vec)
-            mainPart.quad_begin();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i + k < n) {
-                float l = ql.v[k], r = qr.v[k];
-                mainPart.step(l, r);
-                const float mono = 0.5f * (l + r);
-                stats.step(l, r, mono);
-                if constexpr (Main::kHas)
-                    post.step(mono, ana);
-                if constexpr (Pre::kHas) {
-                    pre.step(mono, ana);
-                    prePart.step(l, r, mono);
-                }
-                ql.v[k] = l;
-                qr.v[k] = r;
-            }
-        }
-        if (vec)
-            mainPart.quad_end();
-    };
-    auto quad = [&](Quad& ql, Quad& qr, int i) {
-        quad_math(ql, qr, i);
-        if (mustWrite) {
-            if (!Main::kSeqChannels)
-                store4(dstL, i, n, vec, ql);
-            store4(dstR, i, n, vec, qr);
-        }
-    };
-    if (vec) { // every quad is whole (n % 4 == 0): rows come through the lane's prefetch ring
-        LaneFeed feed;
-        feed.init(srcL, srcR, n);
-        if (Main::kHeavy || !a.octets) {
-#pragma unroll
-            for (int q = 0; q < LF_AHEAD; ++q)
-                feed.issue<false>(q);
-            lf_wait<LF_AHEAD - 1>();
-            Quad ql, qr, nl, nr;
-            feed.read(0, ql, qr);
-#pragma unroll 1
-            for (int i = 0, q = 0; i < n; i += 4, ++q) {
-                feed.issue<false>(q + LF_AHEAD);
-                lf_wait<LF_AHEAD - 1>(); // quads <= q + 1 have landed
-                feed.read(q + 1, nl, nr);
-                quad(ql, qr, i);
-                ql = nl;
-                qr = nr;
-            }
-            lf_wait<0>();
-        } else {
-#pragma unroll
-            for (int q = 0; q < LF_AHEAD; ++q)
-                feed.issue<true>(q);
-            const bool wide = ((reinterpret_cast<uintptr_t>(dstL) | reinterpret_cast<uintptr_t>(dstR)) & 31u) == 0;
-            const int nOct = n >> 3;
-            int q = 0;
-#pragma unroll 1
-            for (int o = 0; o < nOct; ++o, q += 2) {
-                Quad l0, r0, l1, r1;
-                feed.issue<true>(q + LF_AHEAD);
-                feed.issue<true>(q + LF_AHEAD + 1);
-                lf_wait<LF_AHEAD>();     // quads <= q + 1 have landed
-                feed.read(q, l0, r0);
-                feed.read(q + 1, l1, r1);
-                quad_math(l0, r0, 4 * q);
-                quad_math(l1, r1, 4 * q + 4);
-                if (mustWrite) {
-                    if (wide) {
-                        if (!Main::kSeqChannels)
-                            store8(dstL + 4 * q, l0, l1);
-                        store8(dstR + 4 * q, r0, r1);
-                    } else {
-                        if (!Main::kSeqChannels) {
-                            store4(dstL, 4 * q, n, vec, l0);
-                            store4(dstL, 4 * q + 4, n, vec, l1);
-                        }
-                        store4(dstR, 4 * q, n, vec, r0);
-                        store4(dstR, 4 * q + 4, n, vec, r1);
-                    }
-                }
-            }
-            lf_wait<0>();
-            if (n & 4) { // one last quad
-                Quad ql, qr;
-                feed.read(q, ql, qr);
-                quad(ql, qr, 4 * q);
-            }
-        }
-    } else {
-        for (int i = 0; i < n; i += 4) {
-            Quad ql = load4(srcL, i, n, vec);
-            Quad qr = load4(srcR, i, n, vec);
-            quad(ql, qr, i);
-        }
-    }
-
-    if constexpr (Main::kHas) {
-        const SlotDesc& d = a.slot[mainSlot];
-        mainPart.store(L, d);
-        Metrics m = post.finish(L, d.stateBase, stats, n, ana);
-        const float preScore = L.ld(d.stateBase + AV_PRE_SCORE);
-        const float aux = d.kind == K_COHERE ? L.ld(d.stateBase + AV_COUNT + CV_FIT) : 0.0f;
-        publish_record(a, mainSlot, clip, blockAbs, m, preScore, aux);
-    }
-    if constexpr (Pre::kHas) {
-        const SlotDesc& d = a.slot[preSlot];
-        const Metrics m = pre.finish(L, d.stateBase, stats, n, ana);
-        L.st(d.stateBase + AV_PRE_SCORE, m.score);
-        prePart.finish(L, d, n);
-    }
-}
 
 template <class Main>
 __device__ __forceinline__ void sweep_pre_dispatch(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
@@ -1087,8 +45,8 @@ __device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, 
     const SlotDesc& d = a.slot[mainSlot];
     switch (d.kind) {
         case K_INFER: sweep_pre_dispatch<MainInfer>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_PUNCH: sweep_pre_dispatch<MainPunch>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_SAT: sweep_pre_dispatch<MainSat>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_PUNCH: sweep_pre_dispatch<MainPunch<false>>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_SAT: sweep_pre_dispatch<MainSat<false>>(a, clip, mainSlot, pos, n, blockAbs); break;
         case K_WIDTH: sweep_pre_dispatch<MainWidth>(a, clip, mainSlot, pos, n, blockAbs); break;
         case K_COHERE: sweep_pre_dispatch<MainCohere>(a, clip, mainSlot, pos, n, blockAbs); break;
         case K_MOTION: sweep_pre_dispatch<MainMotion>(a, clip, mainSlot, pos, n, blockAbs); break;
@@ -1108,9 +66,10 @@ __device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, 
 
 __global__ void __launch_bounds__(JB_CTA_THREADS, 16) jb_process_kernel(const __grid_constant__ ProcArgs a)
 {
-    const long long clip = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (clip >= a.nClips)
+    const long long lane = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= a.nClips)
         return;
+    const long long clip = a.clipMap != nullptr ? (long long) a.clipMap[lane] : lane;
     int blockAbs = a.histFirstBlock;
     for (int pos = 0; pos < a.nSamples; pos += a.blockSize, ++blockAbs) {
         const int n = min(a.blockSize, a.nSamples - pos);
@@ -1187,6 +146,8 @@ __global__ void jb_synth_kernel(float* audio, int kind, long long firstClip, int
 
 thread_local char g_cudaErr[256];
 long long g_launches = 0;
+// JB_LANE_GENERIC=1: single-plugin launches also take the generic kernel (A/B timing, tests of the generic path)
+const bool g_forceGeneric = [] { const char* v = getenv("JB_LANE_GENERIC"); return v != nullptr && atoi(v) != 0; }();
 
 int check(cudaError_t e, const char* what)
 {
@@ -1197,6 +158,8 @@ int check(cudaError_t e, const char* what)
 }
 
 } // namespace
+
+extern "C" int jbk_launch_single(const ProcArgs* args, int grid, void* stream); // jb_single_light.cu
 
 extern "C" {
 
@@ -1209,8 +172,13 @@ int jbk_launch_process(const ProcArgs* args, void* stream)
     if (args->nClips <= 0 || args->nSamples <= 0)
         return 0;
     const int grid = (args->nClips + JB_CTA_THREADS - 1) / JB_CTA_THREADS;
-    jb_process_kernel<<<grid, JB_CTA_THREADS, 0, (cudaStream_t) stream>>>(*args);
+    cudaStream_t st = (cudaStream_t) stream;
     ++g_launches;
+    if (args->chainLen > 1 && args->exactMath)
+        return check(cudaErrorInvalidValue, "exact math needs one launch per plugin (the fused kernel has the fast routines only)");
+    if (args->chainLen == 1 && (!g_forceGeneric || args->exactMath))
+        return check((cudaError_t) jbk_launch_single(args, grid, stream), "jb_single_kernel launch");
+    jb_process_kernel<<<grid, JB_CTA_THREADS, 0, st>>>(*args);
     return check(cudaGetLastError(), "jb_process_kernel launch");
 }
 

@@ -145,6 +145,8 @@ struct ProcArgs {
     float* widthRing;      // wetR history of the Width slot: element (clip, t) at clip*ringClipStride + t*ringTimeStride
     long long ringClipStride, ringTimeStride; // time-major [ringLen][clipPitch] (1, clipPitch) or clip-major [clip][ringLen] (ringLen, 1)
     float* texWave;        // [2][waveSize][clipPitch]  (Texture waveguides)
+    const int* clipMap;    // lane kernels: lane i of the launch renders clip clipMap[i] (clips sharing one parameter set
+                           // that are not a contiguous range); null = clip i
     long long clipPitch;
     long long rowPitch;    // samples between consecutive (clip, channel) rows of in / out (>= nSamples; a call may
                            // render a time slice [t0, t0 + nSamples) of longer clips, in/out already offset by t0)
@@ -153,6 +155,7 @@ struct ProcArgs {
     int chainLen;
     int recSlotBase, recChainLen; // a launch may render one plugin of a longer chain: its records go to slot recSlotBase + s
                                   // of a record block laid out for recChainLen plugins
+    int exactMath;         // Saturator / Punch: glibc-exact tanh / pow (jb_libm.h) instead of the MUFU-based ones
     int vecOk;             // 16-byte vector path legal (alignment + sizes)
     int octets;            // lane kernel: 8 samples per trip + 32-byte stores (set for big batches of light chains, where
                            // L2 sector throughput is the bound; costs registers, so not for Punch / Texture / Motion chains)

@@ -48,6 +48,7 @@ public:
     int currentProgram() const { return program_; }
     void setProgram(int index);                      // setCurrentProgram(index)
     const char* programName(int index) const;
+    bool operator==(const ParamSet& o) const { return kind_ == o.kind_ && program_ == o.program_ && stored_ == o.stored_ && raw_ == o.raw_; }
 
 private:
     int kind_;

@@ -1,0 +1,40 @@
+// jb_single.cuh -- one plugin per launch: kernel template and launcher shared by the jb_single_*.cu translation units
+// (several, so that nvcc compiles the plugin kernels in parallel).
+#pragma once
+#include "jb_lane.cuh"
+
+namespace {
+
+// One plugin per launch (single-plugin engines, and every launch of a chain rendered plugin by plugin): the same two
+// sweeps per block with the slot index a compile-time 0, one kernel per plugin kind.  What that buys over the generic
+// kernel above: every coefficient is a constant-bank operand (the generic kernel re-read them through a pointer for each
+// sample, `LD.E` -- profiles/r01_s6_tex_lane_before.txt), the code of one plugin is a few thousand instructions instead of
+// 315 k (instruction-cache misses were 18 % of Texture-metal's stall samples), and the register budget is per plugin:
+// MIN_CTAS = 8 gives the heavy plugins 255 registers when the batch is at most 8 warps per SM anyway.
+template <class Main, class Pre, int MIN_CTAS>
+__global__ void __launch_bounds__(JB_CTA_THREADS, MIN_CTAS) jb_single_kernel(const __grid_constant__ ProcArgs a)
+{
+    const long long lane = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= a.nClips)
+        return;
+    const long long clip = a.clipMap != nullptr ? (long long) a.clipMap[lane] : lane;
+    int blockAbs = a.histFirstBlock;
+    for (int pos = 0; pos < a.nSamples; pos += a.blockSize, ++blockAbs) {
+        const int n = min(a.blockSize, a.nSamples - pos);
+        sweep<MainNone, Pre>(a, clip, -1, pos, n, blockAbs);
+        sweep<Main, PreNone>(a, clip, 0, pos, n, blockAbs);
+    }
+}
+
+template <class Main, class Pre>
+cudaError_t launch_single(const ProcArgs& a, int grid, cudaStream_t stream)
+{
+    // warps per SM this batch can supply; the 255-register variant holds at most 8
+    if (Main::kHeavy && grid <= 8 * 148)
+        jb_single_kernel<Main, Pre, 8><<<grid, JB_CTA_THREADS, 0, stream>>>(a);
+    else
+        jb_single_kernel<Main, Pre, 16><<<grid, JB_CTA_THREADS, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+} // namespace

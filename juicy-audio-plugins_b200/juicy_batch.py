@@ -67,6 +67,12 @@ def lib():
         "jb_get_param": (ci, [vp, ci, cs, ctypes.POINTER(cf)]),
         "jb_set_param": (ci, [vp, ci, cs, cf]),
         "jb_set_param_normalised": (ci, [vp, ci, cs, cf]),
+        "jb_set_param_clips": (ci, [vp, ci, ctypes.c_char_p, ctypes.c_float, ci, ci]),
+        "jb_set_program_clips": (ci, [vp, ci, ci, ci, ci]),
+        "jb_get_param_clip": (ci, [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(ctypes.c_float)]),
+        "jb_num_param_sets": (ci, [vp]),
+        "jb_schedule_param": (ci, [vp, ci, ctypes.c_char_p, cll, ctypes.c_float, ci, ci]),
+        "jb_clear_schedule": (ci, [vp]),
         "jb_num_programs": (ci, [vp, ci]),
         "jb_get_program": (ci, [vp, ci]),
         "jb_set_program": (ci, [vp, ci, ci]),
@@ -92,6 +98,7 @@ def lib():
         "jb_copy_to_host": (ci, [ci, vp, vp, ctypes.c_size_t]),
         "jb_kernel_time_ms": (ci, [vp, ctypes.POINTER(cd), ctypes.POINTER(cll)]),
         "jb_set_path": (ci, [vp, ci]),
+        "jb_set_math_mode": (ci, [vp, ci]),
         "jb_path_launches": (ci, [vp, ctypes.POINTER(cll), ctypes.POINTER(cll)]),
     }
     for name, (res, args) in sig.items():
@@ -268,6 +275,30 @@ class BatchProcessor:
     def setValueNotifyingHost(self, pid, normalised, slot=0):
         _check(lib().jb_set_param_normalised(self._h, self.slot(slot), pid.encode(), float(normalised)))
 
+    # ---- per-clip parameters and per-block automation
+    def setParameterClips(self, pid, plain_value, first_clip, n_clips, slot=0):
+        """Give clips [first_clip, first_clip + n_clips) their own value of one parameter."""
+        _check(lib().jb_set_param_clips(self._h, self.slot(slot), pid.encode(), float(plain_value), int(first_clip), int(n_clips)))
+
+    def setCurrentProgramClips(self, index, first_clip, n_clips, slot=0):
+        _check(lib().jb_set_program_clips(self._h, self.slot(slot), int(index), int(first_clip), int(n_clips)))
+
+    def getParameterClip(self, pid, clip, slot=0):
+        v = ctypes.c_float()
+        _check(lib().jb_get_param_clip(self._h, self.slot(slot), pid.encode(), int(clip), ctypes.byref(v)))
+        return v.value
+
+    def numParameterSets(self):
+        return lib().jb_num_param_sets(self._h)
+
+    def scheduleParameter(self, pid, at_block, plain_value, slot=0, first_clip=-1, n_clips=0):
+        """The change takes effect at the top of absolute block `at_block` (host blocks since prepare/reset)."""
+        _check(lib().jb_schedule_param(self._h, self.slot(slot), pid.encode(), int(at_block), float(plain_value),
+                                       int(first_clip), int(n_clips)))
+
+    def clearSchedule(self):
+        _check(lib().jb_clear_schedule(self._h))
+
     def getNumPrograms(self, slot=0):
         return lib().jb_num_programs(self._h, self.slot(slot))
 
@@ -337,6 +368,10 @@ class BatchProcessor:
     def set_path(self, mode):
         """Render-kernel choice: "auto", "lane" (one lane per clip) or "coop" (block-cooperative)."""
         _check(lib().jb_set_path(self._h, {"auto": 0, "lane": 1, "coop": 2}[mode]))
+
+    def set_math_mode(self, mode):
+        """Saturator / Punch tanh and pow: "auto", "exact" (glibc's algorithms, bit-identical) or "fast" (MUFU-based)."""
+        _check(lib().jb_set_math_mode(self._h, {"auto": 0, "exact": 1, "fast": 2}[mode]))
 
     def path_launches(self):
         """(cooperative, lane_per_clip) render-kernel launches so far."""

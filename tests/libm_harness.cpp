@@ -1,0 +1,48 @@
+// Host-side check of csrc/jb_libm.h against the C library (tests/test_libm_restatement.py compiles and runs this with
+// g++ -O2 -ffp-contract=off).  Prints the number of arguments on which the restatement differs from libm, bit for bit.
+#include "jb_libm.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+int main(int argc, char** argv)
+{
+    const long n = argc > 1 ? atol(argv[1]) : 10000000;
+    unsigned s = 0x4A554943u;
+    long badTanh = 0, badPow = 0, nTanh = 0, nPow = 0;
+    for (long i = 0; i < n; ++i) {
+        s = s * 1664525u + 1013904223u;
+        float x;
+        if (i & 1)
+            x = ((s >> 8) / 16777216.0f) * 60.0f - 30.0f;   // the range a driven sample can reach
+        else {
+            x = jblibm::u2f(s);                              // any bit pattern of moderate size (tiny ones included)
+            if (!(fabsf(x) < 80.0f))
+                continue;
+        }
+        ++nTanh;
+        if (jblibm::f2u(tanhf(x)) != jblibm::f2u(jblibm::tanhf_fdlibm(x)))
+            ++badTanh;
+    }
+    for (long i = 0; i < n; ++i) {
+        s = s * 1664525u + 1013904223u;
+        float x;
+        if (i & 1)
+            x = ((s >> 8) / 16777216.0f) * 2.0f;             // Punch's transient: max(0, fast - slow envelope)
+        else {
+            x = jblibm::u2f(s & 0x7fffffffu);
+            if (!(x >= 1.17549435e-38f && x < 1.0e6f))
+                continue;
+        }
+        s = s * 1664525u + 1013904223u;
+        const float y = 0.5f + 0.5f * ((s >> 8) / 16777216.0f); // jmap(slam, 0, 1, 0.95, 0.55) lies inside
+        ++nPow;
+        if (jblibm::f2u(powf(x, y)) != jblibm::f2u(jblibm::powf_glibc_pos(x, y)))
+            ++badPow;
+    }
+    const int zeroOk = jblibm::powf_glibc_pos(0.0f, 0.7f) == powf(0.0f, 0.7f);
+    printf("{\"tanhf_checked\": %ld, \"tanhf_mismatches\": %ld, \"powf_checked\": %ld, \"powf_mismatches\": %ld, \"pow_zero_ok\": %d}\n",
+           nTanh, badTanh, nPow, badPow, zeroOk);
+    return 0;
+}

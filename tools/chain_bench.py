@@ -46,6 +46,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--param", action="append", default=[], help="slot:id=value")
     ap.add_argument("--inplace", action="store_true")
+    ap.add_argument("--clipranges", action="store_true")
+    ap.add_argument("--math", default="auto", choices=("auto", "exact", "fast"))
+    ap.add_argument("--clipmod", default=None, help="id=K: clip c gets parameter id = c mod K in slot 0 (per-clip parameter sets)")
     args = ap.parse_args()
 
     jb = load_juicy_batch()
@@ -60,8 +63,19 @@ def main():
         slot, rest = p.split(":", 1)
         pid, val = rest.split("=")
         eng.setParameter(pid, float(val), int(slot))
+    if args.clipmod:
+        pid, k = args.clipmod.split("=")
+        k = int(k)
+        if args.clipranges:   # K contiguous ranges instead of c mod K
+            per = (n_clips + k - 1) // k
+            for j in range(k):
+                eng.setParameterClips(pid, float(j), j * per, min(per, n_clips - j * per), 0)
+        else:
+            for c in range(n_clips):
+                eng.setParameterClips(pid, float(c % k), c, 1, 0)
     eng.prepareToPlay(48000.0, args.block)
     eng.set_path(args.path)
+    eng.set_math_mode(args.math)
     for _ in range(args.warmup):
         eng.reset()
         eng.process_device(d_in.ptr.value, d_out.ptr.value, n)
