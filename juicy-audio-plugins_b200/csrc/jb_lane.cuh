@@ -119,13 +119,17 @@ struct Lane {
 struct BlockStats {
     float rms = 0.0f, peak = 0.0f, side = 0.0f, corr = 0.0f;
     double l2 = 0.0, r2 = 0.0;
+    // Plain sums that feed the metrics record only (tolerance 0.01 absolute): fused multiply-adds, one instruction per
+    // sum.  getRMSLevel's two sums of squares stay in fp64 like the shim's: fp32 would do for the tolerance, but measured
+    // on 65536 clips (profiles/r01_s6_light_variants.txt) the fp32 form made the Infer kernel 1.6x SLOWER (21.3 -> 35.3 ms,
+    // stalls move to the cp.async ring: long_scoreboard 32 %, mio 26 %) and nothing else faster, so the DFMAs stay.
     __device__ __forceinline__ void step(float l, float r, float mono)
     {
-        rms += mono * mono;                 // rmsAccum; midAccum is the same expression (:62, :86, :88)
-        peak = jmaxf(peak, fabsf(mono));
+        rms = fmaf(mono, mono, rms);        // rmsAccum; midAccum is the same expression (:62, :86, :88)
+        peak = fmaxf(peak, fabsf(mono));
         const float s = 0.5f * (l - r);
-        side += s * s;
-        corr += l * r;
+        side = fmaf(s, s, side);
+        corr = fmaf(l, r, corr);
         const double dl = (double) l, dr = (double) r;
         l2 = fma(dl, dl, l2);               // dl*dl is exact in fp64, so the fused form rounds identically
         r2 = fma(dr, dr, r2);
@@ -194,13 +198,10 @@ struct MainInfer : MainBase {
     }
     __device__ __forceinline__ void step(float& l, float& r)
     {
-        if (mode == 1) {
-            l *= g;
-            r *= g;
-        } else if (mode == 2) {
-            l = 0.0f;
-            r = 0.0f;
-        }
+        // selects, not branches: the quad stays one basic block (mode 0 keeps the sample's bits, like applyGain(1))
+        const float gl = l * g, gr = r * g;
+        l = mode == 1 ? gl : (mode == 2 ? 0.0f : l);
+        r = mode == 1 ? gr : (mode == 2 ? 0.0f : r);
     }
     __device__ __forceinline__ void store(const Lane&, const SlotDesc&) {}
     __device__ __forceinline__ bool writes(bool outOfPlace) const { return mode != 0 || outOfPlace; }
@@ -467,6 +468,7 @@ struct MainTexture : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
     static constexpr bool kHeavy = true; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     TexChan ch0, ch1;
+    float a1Rest[4]; // metal: 2 r cos(theta) of the unbent modes (impact == 0)
     uint32_t rng0, rng1;
     int waveIdx;
     const TexCoef* c;
@@ -493,6 +495,11 @@ struct MainTexture : MainBase {
         rng1 = accA * rng0 + accC;
         wave = L.a.texWave + L.clip;
         pitch = L.a.clipPitch;
+        if (MAT == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                a1Rest[k] = metalA1(k, 1.0f); // bend = 1 + 0.09 * 0
+        }
     }
 
     // modeStep with block-constant pole radius (:77-89); a1 is passed in
@@ -562,7 +569,9 @@ struct MainTexture : MainBase {
     }
     __device__ __forceinline__ void quad_end() { havePref = false; }
 
-    __device__ __forceinline__ float one(float dry, TexChan& st, uint32_t& rng, float* line, float delayed) const
+    // Per-sample front part (:116-134): transient envelope -> impact / body / trail, three-band split -> core
+    struct Front { float impact, body, trail, core; };
+    __device__ __forceinline__ Front front(float dry, TexChan& st) const
     {
         const TexCoef& k = *c;
         const float driven = dry * k.inTrim;
@@ -581,7 +590,14 @@ struct MainTexture : MainBase {
         const float high = (driven - st.hp);
         const float mid = driven - st.lp - high;
         const float core = low + mid + high * k.highTilt;
-
+        return Front { impact, body, trail, core };
+    }
+    // a1: the four modes' 2 r cos(theta) of this sample (metal only)
+    __device__ __forceinline__ float back(float dry, TexChan& st, uint32_t& rng, float* line, float delayed, const Front& f,
+                                          const float* a1) const
+    {
+        const TexCoef& k = *c;
+        const float impact = f.impact, body = f.body, trail = f.trail, core = f.core;
         float shaped;
         if (MAT == 0) { // gel :137-151
             const float zeta = jmap3(trail, 0.62f, 1.45f);
@@ -594,11 +610,10 @@ struct MainTexture : MainBase {
             shaped = tanhf(shaped * k.shapeGain);
         } else if (MAT == 1) { // metal :152-169
             const float exc = core * (0.19f + 0.52f * impact);
-            const float bend = 1.0f + 0.09f * impact;
-            const float m0 = mode(st, 0, exc, metalA1(0, bend));
-            const float m1 = mode(st, 1, exc, metalA1(1, bend));
-            const float m2 = mode(st, 2, exc, metalA1(2, bend));
-            const float m3 = mode(st, 3, exc, metalA1(3, bend));
+            const float m0 = mode(st, 0, exc, a1[0]);
+            const float m1 = mode(st, 1, exc, a1[1]);
+            const float m2 = mode(st, 2, exc, a1[2]);
+            const float m3 = mode(st, 3, exc, a1[3]);
             const float modes = m0 + m1 + m2 + m3;
             const float brightExcite = 0.03f * impact * (core - st.hp);
             shaped = (0.44f * core + 0.42f * modes + brightExcite) * k.shapeGain;
@@ -681,8 +696,30 @@ struct MainTexture : MainBase {
                 d1 = waveRead(line1);
             }
         }
-        l = one(l, ch0, rng0, line0, d0);
-        r = one(r, ch1, rng1, line1, d1);
+        const Front f0 = front(l, ch0), f1 = front(r, ch1);
+        float a1L[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, a1R[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+        if (MAT == 1) {
+            // The poles bend with the transient (`bend = 1 + 0.09 impact`, :157-158), which costs a std::cos per mode,
+            // channel and sample -- but impact is exactly 0 whenever the sample does not exceed its envelope, and then
+            // the angle is the block-constant one of load().  Taken only when that holds for every lane of the warp
+            // (a warp-uniform branch; same expression, same bits): between the hits of an impulse train or a drum tail
+            // that is nearly always.
+            const bool rest = __all_sync(__activemask(), f0.impact == 0.0f && f1.impact == 0.0f);
+            if (rest) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    a1L[k] = a1R[k] = a1Rest[k];
+            } else {
+                const float bendL = 1.0f + 0.09f * f0.impact, bendR = 1.0f + 0.09f * f1.impact;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    a1L[k] = metalA1(k, bendL);
+                    a1R[k] = metalA1(k, bendR);
+                }
+            }
+        }
+        l = back(l, ch0, rng0, line0, d0, f0, a1L);
+        r = back(r, ch1, rng1, line1, d1, f1, a1R);
         if (MAT == 2 || MAT == 3)
             waveIdx = waveIdx + 1 == c->waveSize ? 0 : waveIdx + 1;
     }
@@ -916,7 +953,13 @@ __device__ __forceinline__ void store4(float* p, int i, int n, bool vec, const Q
 // its rows with cp.async (no register landing, no scoreboard wait) into a private 2 x 32-sample ring
 // in shared memory 24 samples ahead of use and reads them back one quad ahead.  Piece k of a row is
 // stored at k ^ (lane & 7) so that the 8 lanes of a quarter-warp hit 8 different bank groups.
-constexpr int LF_AHEAD = 6; // quads in flight per row (ring: 8 quads = 128 B per row, 8 KB per warp: 16+ warps per SM stay resident)
+#ifndef JB_LF_RING
+#define JB_LF_RING 8   // quads per row in a lane's ring (8: 128 B per row, 8 KB per warp, 16+ warps per SM stay resident)
+#endif
+#ifndef JB_LF_AHEAD
+#define JB_LF_AHEAD 6  // quads in flight per row (<= JB_LF_RING - 2: the octet loop issues two before it waits)
+#endif
+constexpr int LF_RING = JB_LF_RING, LF_AHEAD = JB_LF_AHEAD;
 
 __device__ __forceinline__ uint32_t lf_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 // CACHE_L1: the 32-byte sector a piece belongs to is kept in L1, so the row's next piece does not go to L2 again
@@ -944,8 +987,8 @@ struct LaneFeed {
     int nQuads;
     __device__ __forceinline__ void init(const float* l, const float* r, int n)
     {
-        __shared__ __align__(256) float4 ring[JB_LANE_CTA_THREADS * 16];
-        base = lf_smem_u32(&ring[threadIdx.x * 16]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
+        __shared__ __align__(256) float4 ring[JB_LANE_CTA_THREADS * 2 * LF_RING];
+        base = lf_smem_u32(&ring[threadIdx.x * 2 * LF_RING]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
         asm volatile("" : "+r"(base));
         srcL = l;
         srcR = r;
@@ -955,17 +998,17 @@ struct LaneFeed {
     __device__ __forceinline__ void issue(int q) const // quad q of both rows -> ring piece q & 7; always commits a group
     {
         if (q < nQuads) {
-            const uint32_t off = (uint32_t) (q & 7) << 4;
+            const uint32_t off = (uint32_t) (q & (LF_RING - 1)) << 4;
             lf_cp_async16<CACHE_L1>(base ^ off, srcL + 4 * q);
-            lf_cp_async16<CACHE_L1>((base ^ off) + 128u, srcR + 4 * q);
+            lf_cp_async16<CACHE_L1>((base ^ off) + 16u * LF_RING, srcR + 4 * q);
         }
         lf_commit();
     }
     __device__ __forceinline__ void read(int q, Quad& l, Quad& r) const
     {
-        const uint32_t off = (uint32_t) (q & 7) << 4;
+        const uint32_t off = (uint32_t) (q & (LF_RING - 1)) << 4;
         l = lf_lds(base ^ off);
-        r = lf_lds((base ^ off) + 128u);
+        r = lf_lds((base ^ off) + 16u * LF_RING);
     }
 };
 

@@ -116,6 +116,29 @@ public:
             check(jb_get_history(e_, slot, firstBlock, nBlocks, out.data()));
         return out;
     }
+    // per-instance settings and host automation: the reference re-reads its parameters every block
+    void setParameterForClips(int slot, const char* id, float plain, int firstClip, int nClips)
+    {
+        check(jb_set_param_clips(e_, slot, id, plain, firstClip, nClips));
+    }
+    void setCurrentProgramForClips(int slot, int index, int firstClip, int nClips)
+    {
+        check(jb_set_program_clips(e_, slot, index, firstClip, nClips));
+    }
+    float getRawParameterValueOfClip(int slot, const char* id, int clip) const
+    {
+        float v = 0.0f;
+        check(jb_get_param_clip(e_, slot, id, clip, &v));
+        return v;
+    }
+    // takes effect at the top of absolute host block `atBlock` (counted since prepareToPlay), like
+    // setValueNotifyingHost between two processBlock callbacks
+    void scheduleParameter(int slot, const char* id, long long atBlock, float plain, int firstClip = JB_ALL_CLIPS, int nClips = 0)
+    {
+        check(jb_schedule_param(e_, slot, id, atBlock, plain, firstClip, nClips));
+    }
+    void setMathMode(int mode) { check(jb_set_math_mode(e_, mode)); }
+
     // JuicyMeterPanel state of every clip after the render (src/shared/JuicyMeterPanel.cpp:9-34,54-71)
     std::vector<jb_meter_stats> getMeterStatistics(int slot, int firstBlock, int nBlocks, int blockStride = 1)
     {
