@@ -147,6 +147,12 @@ __global__ void jb_synth_kernel(float* audio, int kind, long long firstClip, int
 thread_local char g_cudaErr[256];
 long long g_launches = 0;
 // JB_LANE_GENERIC=1: single-plugin launches also take the generic kernel (A/B timing, tests of the generic path)
+const int g_pairMode = [] { const char* v = getenv("JB_PAIR"); return v == nullptr ? -1 : atoi(v); }();
+int envInt(const char* name, int dflt) { const char* v = getenv(name); return v == nullptr ? dflt : atoi(v); }
+// measured (profiles/r01_s6_pair.txt): Texture 8192 clips 1.5-1.7x faster in pairs, 16384 1.1x, 32768 0.9x; Saturator / Punch
+// with the MUFU math 1.4x at 8192, 0.9x at 16384; with the exact routines (long per-channel chains) faster at every size
+const int g_pairLimitTexture = envInt("JB_PAIR_LIMIT_TEXTURE", 16384), g_pairLimitExact = envInt("JB_PAIR_LIMIT_EXACT", 1 << 30),
+          g_pairLimitFast = envInt("JB_PAIR_LIMIT_FAST", 10240);
 const bool g_forceGeneric = [] { const char* v = getenv("JB_LANE_GENERIC"); return v != nullptr && atoi(v) != 0; }();
 
 int check(cudaError_t e, const char* what)
@@ -160,6 +166,8 @@ int check(cudaError_t e, const char* what)
 } // namespace
 
 extern "C" int jbk_launch_single(const ProcArgs* args, int grid, void* stream); // jb_single_light.cu
+extern "C" int jbk_pair_supported(const ProcArgs* args);                          // jb_pair.cu
+extern "C" int jbk_launch_pair(const ProcArgs* args, void* stream);
 
 extern "C" {
 
@@ -176,8 +184,18 @@ int jbk_launch_process(const ProcArgs* args, void* stream)
     ++g_launches;
     if (args->chainLen > 1 && args->exactMath)
         return check(cudaErrorInvalidValue, "exact math needs one launch per plugin (the fused kernel has the fast routines only)");
-    if (args->chainLen == 1 && (!g_forceGeneric || args->exactMath))
+    if (args->chainLen == 1 && (!g_forceGeneric || args->exactMath)) {
+        // Two lanes per clip (jb_pair.cu) while the batch is too small to keep the schedulers busy with one: measured
+        // crossovers in profiles/r01_s6_pair.txt.  JB_PAIR=0 / 1 forces a choice.
+        if (jbk_pair_supported(args)) {
+            const int kind = args->slot[0].kind;
+            const int limit = kind == K_TEXTURE ? g_pairLimitTexture : (args->exactMath ? g_pairLimitExact : g_pairLimitFast);
+            const bool pair = g_pairMode < 0 ? args->nClips <= limit : g_pairMode != 0;
+            if (pair)
+                return check((cudaError_t) jbk_launch_pair(args, stream), "jb_pair_kernel launch");
+        }
         return check((cudaError_t) jbk_launch_single(args, grid, stream), "jb_single_kernel launch");
+    }
     jb_process_kernel<<<grid, JB_CTA_THREADS, 0, st>>>(*args);
     return check(cudaGetLastError(), "jb_process_kernel launch");
 }

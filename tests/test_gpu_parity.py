@@ -322,3 +322,51 @@ def test_lane_kernel_split_chain_equals_fused_chain(jb, monkeypatch):
     assert np.array_equal(fused, split)
     for a, b in zip(hist_fused, hist_split):
         assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------ two lanes per clip (csrc/jb_pair.cu)
+
+PAIR_CASES = [("JuicySaturator", (), "fast"), ("JuicySaturator", (), "exact"), ("JuicyPunch", (), "fast"), ("JuicyPunch", (), "exact")] + \
+             [("JuicyTexture", ((0, "material", float(m)),), "auto") for m in range(5)]
+
+
+@pytest.mark.parametrize("plugin,settings,math", PAIR_CASES,
+                         ids=["sat-fast", "sat-exact", "punch-fast", "punch-exact"] + ["texture-%s" % m for m in ("gel", "metal", "wood", "plastic", "flesh")])
+def test_pair_kernel_is_bit_identical_to_the_one_lane_kernel(plugin, settings, math, jb, port, monkeypatch):
+    """Channel-per-lane kernel == clip-per-lane kernel, samples and every record of every block, bit for bit;
+    49 clips (a partial warp, odd count), ragged split into two calls; and both match the oracle."""
+    import juicy_batch  # noqa: F401  (the library reads JB_PAIR once, at load: spawn fresh interpreters)
+    import subprocess, sys, os, tempfile, json
+    n_clips, n = 49, 5 * BLOCK
+    code = r'''
+import sys, os, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import load_juicy_batch
+jb = load_juicy_batch()
+clips = jb.synth_clips("mixed", 17, %d, %d)
+clips *= np.linspace(0.3, 1.8, %d, dtype=np.float32)[:, None, None]
+eng = jb.BatchProcessor([%r], %d)
+for slot, pid, v in %r:
+    eng.setParameter(pid, v, slot)
+eng.set_path("lane"); eng.set_math_mode(%r)
+eng.prepareToPlay(48000.0, 512); eng.enableHistory(16)
+a = eng.processBlock(clips[:, :, :1024]); b = eng.processBlock(clips[:, :, 1024:])
+np.savez(sys.argv[1], out=np.concatenate([a, b], axis=2), hist=eng.getHistory(0), clips=clips)
+''' % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+       n_clips, n, n_clips, plugin, n_clips, list(settings), math)
+    res = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for mode in ("0", "1"):
+            path = os.path.join(tmp, "m%s.npz" % mode)
+            env = dict(os.environ, JB_PAIR=mode)
+            subprocess.check_call([sys.executable, "-c", code, path], env=env)
+            res[mode] = dict(np.load(path))
+    assert np.array_equal(res["0"]["out"].view(np.uint32), res["1"]["out"].view(np.uint32)), \
+        "max diff %g" % float(np.abs(res["0"]["out"] - res["1"]["out"]).max())
+    assert np.array_equal(res["0"]["hist"].view(np.uint32), res["1"]["hist"].view(np.uint32))
+    clips = res["1"]["clips"]
+    params = {0: {pid: v for _, pid, v in settings}} if settings else None
+    for c in (0, 7, 48):
+        ref, h = port.run_chain([plugin], clips[c], sample_rate=SAMPLE_RATE, block_size=BLOCK, params=params)
+        assert_samples_close(res["1"]["out"][c], ref, "%s clip %d" % (plugin, c))
+        assert_records_close(res["1"]["hist"][:, c, :], h[0], "%s clip %d" % (plugin, c))
