@@ -299,6 +299,23 @@ int resetState(jb_engine* e)
     return JB_OK;
 }
 
+// Sample-streaming mode of one plugin's lane launch: 0 = four samples per trip through the lane's cp.async ring; 1 = eight,
+// 32-byte stores, L1-cached row pieces (light plugins, >= 32768 clips: L2 sector throughput); 2 = warp-transposed tile
+// streaming (jb_lane.cuh).  Measured (profiles/r01_s6_tile.txt): the tile wins where nothing is written back -- Infer,
+// 16384 clips 7.0 -> 5.6 ms, 65536 clips out of place 19.3 -> 16.5 ms -- and loses for the plugins that store every sample
+// (Saturator 65536 clips 20.0 -> 23.8 ms), so only Infer takes it.  JB_TILE=0 / 1 forces it off / on for light plugins.
+int octetsFor(int kind, int nClips, int nSamples, bool mapped)
+{
+    static const int tileMode = [] { const char* v = std::getenv("JB_TILE"); return v == nullptr ? -1 : std::atoi(v); }();
+    if (mapped || kind == jb::kPunch || kind == jb::kTexture || kind == jb::kMotion)
+        return 0;
+    const bool tileOk = nClips % 32 == 0 && nSamples % 4 == 0;
+    const bool tile = tileMode < 0 ? (kind == jb::kInfer && nClips >= 8192) : tileMode != 0;
+    if (tileOk && tile)
+        return 2;
+    return nClips >= 32768 ? 1 : 0;
+}
+
 int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params, const float* dIn, float* dOut, int nSamples,
               int nClips, long long clipOffset, long long rowPitch = 0)
 {
@@ -325,10 +342,14 @@ int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params
     a.recChainLen = a.chainLen;
     const bool aligned = ((reinterpret_cast<uintptr_t>(dIn) | reinterpret_cast<uintptr_t>(dOut)) & 15u) == 0;
     a.vecOk = (aligned && nSamples % 4 == 0 && a.rowPitch % 4 == 0 && e->blockSize % 4 == 0) ? 1 : 0;
-    a.octets = nClips >= 32768 ? 1 : 0;
-    for (int k : e->chain)
-        if (k == jb::kPunch || k == jb::kTexture || k == jb::kMotion)
-            a.octets = 0;
+    a.lightOctets = 0; // per launch, see octetsFor()
+    a.octets = e->chain.size() == 1 ? octetsFor(e->chain[0], nClips, nSamples, false) : 0;
+    if (e->chain.size() > 1) { // fused generic kernel: eight samples per trip only when every plugin is light
+        a.octets = nClips >= 32768 ? 1 : 0;
+        for (int k : e->chain)
+            if (k == jb::kPunch || k == jb::kTexture || k == jb::kMotion)
+                a.octets = 0;
+    }
     {   // Saturator / Punch transcendentals: the MUFU-based ones are within 3e-6 of the reference, which Texture's metal /
         // wood / plastic resonators amplify ~200x; with a Texture further down the chain they run the C library's own
         // algorithms (jb_libm.h) so that its input is the reference's, bit for bit.
@@ -436,8 +457,7 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
             one.slot[0] = a.slot[s];
             one.recSlotBase = s;
             one.recChainLen = L;
-            one.octets = a.clipMap == nullptr && a.nClips >= 32768
-                         && !(one.slot[0].kind == jb::kPunch || one.slot[0].kind == jb::kTexture || one.slot[0].kind == jb::kMotion);
+            one.octets = octetsFor(one.slot[0].kind, a.nClips, a.nSamples, a.clipMap != nullptr);
             if (jbk_launch_process(&one, stream) != 0)
                 return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
         }
@@ -620,6 +640,7 @@ int renderClips(jb_engine* e, const float* dIn, float* dOut, int ns, int nc, lon
             buildArgs(e, a, paramsOfSet(e, g.set), dIn - c0 * clipStride, dOut - c0 * clipStride, ns, (int) (i1 - i0), 0, rowPitch);
             a.clipMap = e->dClipMap + g.mapOffset + (i0 - m);
             a.octets = 0;
+            a.lightOctets = 0;
         }
         cudaStream_t st = e->stream;
         if (!serial) {

@@ -196,7 +196,7 @@ int jbk_launch_process(const ProcArgs* args, void* stream)
         }
         return check((cudaError_t) jbk_launch_single(args, grid, stream), "jb_single_kernel launch");
     }
-    jb_process_kernel<<<grid, JB_CTA_THREADS, 0, st>>>(*args);
+    jb_process_kernel<<<grid, JB_CTA_THREADS, lane_smem_bytes(args->octets), st>>>(*args);
     return check(cudaGetLastError(), "jb_process_kernel launch");
 }
 

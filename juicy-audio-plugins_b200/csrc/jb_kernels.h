@@ -157,6 +157,7 @@ struct ProcArgs {
                                   // of a record block laid out for recChainLen plugins
     int exactMath;         // Saturator / Punch: glibc-exact tanh / pow (jb_libm.h) instead of the MUFU-based ones
     int vecOk;             // 16-byte vector path legal (alignment + sizes)
+    int lightOctets;       // the `octets` mode a light plugin's launch of this call uses (chains rendered plugin by plugin)
     int octets;            // lane kernel: 8 samples per trip + 32-byte stores (set for big batches of light chains, where
                            // L2 sector throughput is the bound; costs registers, so not for Punch / Texture / Motion chains)
     AnaCoef ana;

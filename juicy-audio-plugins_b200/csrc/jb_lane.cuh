@@ -231,10 +231,21 @@ struct MainSat : MainBase {
         const float wet = state * c.outGain;
         return dry + c.mix * (wet - dry);
     }
+    // both channels in packed halves (jb_device.cuh: F2): the same operations in the same order as one()
     __device__ __forceinline__ void step(float& l, float& r)
     {
-        l = one(l, s0);
-        r = one(r, s1);
+        const F2 dry = f2(l, r);
+        const F2 driven = mul2(dry, f2(c.inGain));
+        const F2 skewed = mul_add2(mul2(f2(c.asym), driven), driven, driven);
+        const F2 soft = EXACT ? f2(jblibm::tanhf_fdlibm(skewed.x), jblibm::tanhf_fdlibm(skewed.y)) : tanh_fast2(skewed);
+        F2 st = f2(s0, s1);
+        st = mul_add2(f2(c.toneCoeff), sub2(soft, st), st);
+        s0 = st.x;
+        s1 = st.y;
+        const F2 wet = mul2(st, f2(c.outGain));
+        const F2 out = mul_add2(f2(c.mix), f2(wet.x - dry.x, wet.y - dry.y), dry);
+        l = out.x;
+        r = out.y;
     }
     __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
     {
@@ -981,13 +992,32 @@ __device__ __forceinline__ Quad lf_lds(uint32_t addr)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]) : "r"(addr) : "memory");
     return q;
 }
+// One static shared buffer per CTA (= warp), used either as the lanes' private rings (LaneFeed, 8 KB) or as the warp's
+// three-stage tile (tile streaming below, 15 KB)
+constexpr int TILE_PITCH = 20;                          // floats per (row, stage): 16 samples + 4 pad -> conflict-free LDS.128
+constexpr int TILE_STAGE_BYTES = 64 * TILE_PITCH * 4;   // 64 rows (2 channels x 32 clips)
+constexpr int TILE_STAGES = 3;
+__device__ __forceinline__ float4* lane_smem()
+{
+    extern __shared__ __align__(256) float4 jb_lane_dynamic_smem[]; // lane_smem_bytes(octets) at launch
+    return jb_lane_dynamic_smem;
+}
+inline size_t lane_smem_bytes(int octets)
+{
+    return octets == 2 ? (size_t) TILE_STAGES * TILE_STAGE_BYTES : (size_t) JB_LANE_CTA_THREADS * 2 * LF_RING * 16;
+}
+__device__ __forceinline__ void lf_sts(uint32_t addr, const Quad& q)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(q.v[0]), "f"(q.v[1]), "f"(q.v[2]), "f"(q.v[3]) : "memory");
+}
+
 struct LaneFeed {
     uint32_t base;           // shared address of this lane's 256-byte ring (row L, then row R), swizzle folded in
     const float *srcL, *srcR;
     int nQuads;
     __device__ __forceinline__ void init(const float* l, const float* r, int n)
     {
-        __shared__ __align__(256) float4 ring[JB_LANE_CTA_THREADS * 2 * LF_RING];
+        float4* ring = lane_smem();
         base = lf_smem_u32(&ring[threadIdx.x * 2 * LF_RING]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
         asm volatile("" : "+r"(base));
         srcL = l;
@@ -1099,7 +1129,76 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
     };
     constexpr std::true_type kWhole {};
     constexpr std::false_type kRagged {};
-    if (vec) { // every quad is whole (n % 4 == 0): rows come through the lane's prefetch ring
+    if (vec && a.octets == 2 && !Main::kHeavy) {
+        // Warp-transposed tile streaming (big batches of light plugins).  With one row per lane every 16-byte request of a
+        // warp touches 32 different lines: 32 L1TEX wavefronts per LDGSTS / per store, and the L1TEX pipe, not HBM and
+        // not instruction issue, was the bound (l1tex__throughput 80 %, profiles/r01_s6_single_ncu.md).  Here the warp loads
+        // its 64 rows 16 samples at a time with requests that cover 8 rows x 64 contiguous bytes (8 lines per request),
+        // into a three-stage tile [channel][clip][16 + 4 pad] in shared memory; each lane then walks its own two rows
+        // out of the tile (conflict-free LDS.128) and stores its results directly, 32 bytes per row at a time (sending
+        // them back through the tile for 8-rows-per-request stores was measured slower: profiles/r01_s6_tile.txt).
+        // All synchronisation is intra-warp (cp.async groups + __syncwarp).
+        const uint32_t tileS = lf_smem_u32(lane_smem());
+        const int lane = threadIdx.x;
+        const uint32_t laneOff = (uint32_t) ((lane >> 2) * (TILE_PITCH * 4) + (lane & 3) * 16);
+        const uint32_t myL = (uint32_t) (lane * TILE_PITCH * 4), myR = (uint32_t) ((32 + lane) * TILE_PITCH * 4);
+        const float* srcBase = firstRead ? a.in : a.out;
+        long long rowOff[8]; // element offset of the 16-byte piece this lane moves in request j
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int srow = j * 8 + (lane >> 2);
+            const long long cj = __shfl_sync(0xffffffffu, clip, srow & 31);
+            rowOff[j] = (cj * a.nCh + (srow >> 5)) * a.rowPitch + pos + (lane & 3) * 4;
+        }
+        const int nStages = n >> 4;
+        const bool wide = ((reinterpret_cast<uintptr_t>(dstL) | reinterpret_cast<uintptr_t>(dstR)) & 31u) == 0;
+        auto issue = [&](int k, int slot) {
+            if (k < nStages) {
+                const uint32_t st = tileS + (uint32_t) slot * TILE_STAGE_BYTES + laneOff;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    lf_cp_async16<false>(st + (uint32_t) j * (8 * TILE_PITCH * 4), srcBase + rowOff[j] + 16 * k);
+            }
+            lf_commit();
+        };
+        issue(0, 0);
+        issue(1, 1);
+        int slot = 0;
+#pragma unroll 1
+        for (int k = 0; k < nStages; ++k) {
+            issue(k + 2, slot == 0 ? 2 : slot - 1); // (k + 2) % 3; that slot was drained by the previous iteration
+            lf_wait<2>();                            // stage k has landed
+            __syncwarp();
+            const uint32_t st = tileS + (uint32_t) slot * TILE_STAGE_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { // eight samples at a time; results leave with one 32-byte store per row
+                Quad l0 = lf_lds(st + myL + h * 32), r0 = lf_lds(st + myR + h * 32);
+                Quad l1 = lf_lds(st + myL + h * 32 + 16), r1 = lf_lds(st + myR + h * 32 + 16);
+                const int i = 16 * k + 8 * h;
+                quad_math(l0, r0, i, kWhole);
+                quad_math(l1, r1, i + 4, kWhole);
+                if (mustWrite) {
+                    if (wide) {
+                        store8(dstL + i, l0, l1);
+                        store8(dstR + i, r0, r1);
+                    } else {
+                        store4(dstL, i, n, vec, l0);
+                        store4(dstL, i + 4, n, vec, l1);
+                        store4(dstR, i, n, vec, r0);
+                        store4(dstR, i + 4, n, vec, r1);
+                    }
+                }
+            }
+            __syncwarp(); // before this slot is refilled
+            slot = slot == 2 ? 0 : slot + 1;
+        }
+        lf_wait<0>();
+        for (int i = nStages << 4; i < n; i += 4) { // the block's last 4 .. 12 samples, straight from global memory
+            Quad ql = load4(srcL, i, n, vec);
+            Quad qr = load4(srcR, i, n, vec);
+            quad(ql, qr, i, kWhole);
+        }
+    } else if (vec) { // every quad is whole (n % 4 == 0): rows come through the lane's prefetch ring
         LaneFeed feed;
         feed.init(srcL, srcR, n);
         if (Main::kHeavy || !a.octets) {

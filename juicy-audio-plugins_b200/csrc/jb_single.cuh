@@ -31,9 +31,9 @@ cudaError_t launch_single(const ProcArgs& a, int grid, cudaStream_t stream)
 {
     // warps per SM this batch can supply; the 255-register variant holds at most 8
     if (Main::kHeavy && grid <= 8 * 148)
-        jb_single_kernel<Main, Pre, 8><<<grid, JB_CTA_THREADS, 0, stream>>>(a);
+        jb_single_kernel<Main, Pre, 8><<<grid, JB_CTA_THREADS, lane_smem_bytes(a.octets), stream>>>(a);
     else
-        jb_single_kernel<Main, Pre, 16><<<grid, JB_CTA_THREADS, 0, stream>>>(a);
+        jb_single_kernel<Main, Pre, 16><<<grid, JB_CTA_THREADS, lane_smem_bytes(a.octets), stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -330,6 +330,57 @@ PAIR_CASES = [("JuicySaturator", (), "fast"), ("JuicySaturator", (), "exact"), (
              [("JuicyTexture", ((0, "material", float(m)),), "auto") for m in range(5)]
 
 
+def _render_in_fresh_process(env, chain, settings, math, n_clips, n, tmp, tag):
+    """The library reads its kernel-choice environment once, at load: render in a fresh interpreter."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, os, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import load_juicy_batch
+jb = load_juicy_batch()
+clips = jb.synth_clips("mixed", 17, %d, %d)
+clips *= np.linspace(0.3, 1.8, %d, dtype=np.float32)[:, None, None]
+chain = %r
+eng = jb.BatchProcessor(chain, %d)
+for slot, pid, v in %r:
+    eng.setParameter(pid, v, slot)
+eng.set_path("lane"); eng.set_math_mode(%r)
+eng.prepareToPlay(48000.0, 512); eng.enableHistory(16)
+a = eng.processBlock(clips[:, :, :1024]); b = eng.processBlock(clips[:, :, 1024:])
+np.savez(sys.argv[1], out=np.concatenate([a, b], axis=2), clips=clips, **{"hist%%d" %% s: eng.getHistory(s) for s in range(len(chain))})
+''' % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+       n_clips, n, n_clips, list(chain), n_clips, list(settings), math)
+    path = os.path.join(tmp, "%s.npz" % tag)
+    subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, **env))
+    return dict(np.load(path))
+
+
+@pytest.mark.parametrize("chain", [["JuicySaturator"], ["JuicyCohere"], ["JuicyWidth"], ["JuicyInfer"],
+                                   ["JuicySaturator", "JuicyWidth", "JuicyCohere", "JuicyInfer"]],
+                         ids=["saturator", "cohere", "width", "infer", "light-chain"])
+def test_tile_streaming_is_bit_identical_to_lane_streaming(chain, jb, port):
+    """Warp-transposed tile streaming (JB_TILE=1; default from 32768 clips) == per-lane ring streaming (JB_TILE=0):
+    same arithmetic, only the way samples travel differs.  64 clips, 5 blocks + a 12-sample tail in two calls."""
+    import tempfile
+    n_clips, n = 64, 5 * BLOCK + 12
+    settings = [(chain.index("JuicyInfer"), "trim", 3.0)] if chain == ["JuicyInfer"] else []
+    with tempfile.TemporaryDirectory() as tmp:
+        res = {m: _render_in_fresh_process({"JB_TILE": m}, chain, settings, "fast", n_clips, n, tmp, "t" + m) for m in ("0", "1")}
+    assert np.array_equal(res["0"]["out"].view(np.uint32), res["1"]["out"].view(np.uint32)), \
+        "max diff %g" % float(np.abs(res["0"]["out"] - res["1"]["out"]).max())
+    for s in range(len(chain)):
+        assert np.array_equal(res["0"]["hist%d" % s].view(np.uint32), res["1"]["hist%d" % s].view(np.uint32)), s
+    clips = res["1"]["clips"]
+    params = {s: {pid: v} for s, pid, v in settings} if settings else None
+    for c in (0, 31, 63):
+        ref, h = port.run_chain(chain, clips[c], sample_rate=SAMPLE_RATE, block_size=BLOCK, params=params)
+        assert_samples_close(res["1"]["out"][c], ref, "clip %d" % c)
+        for s in range(len(chain)):
+            assert_records_close(res["1"]["hist%d" % s][:, c, :], h[s], "clip %d slot %d" % (c, s))
+
+
 @pytest.mark.parametrize("plugin,settings,math", PAIR_CASES,
                          ids=["sat-fast", "sat-exact", "punch-fast", "punch-exact"] + ["texture-%s" % m for m in ("gel", "metal", "wood", "plastic", "flesh")])
 def test_pair_kernel_is_bit_identical_to_the_one_lane_kernel(plugin, settings, math, jb, port, monkeypatch):
