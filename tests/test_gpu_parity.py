@@ -421,3 +421,26 @@ np.savez(sys.argv[1], out=np.concatenate([a, b], axis=2), hist=eng.getHistory(0)
         ref, h = port.run_chain([plugin], clips[c], sample_rate=SAMPLE_RATE, block_size=BLOCK, params=params)
         assert_samples_close(res["1"]["out"][c], ref, "%s clip %d" % (plugin, c))
         assert_records_close(res["1"]["hist"][:, c, :], h[0], "%s clip %d" % (plugin, c))
+
+
+@pytest.mark.parametrize("sr,block", [(44100.0, 512), (96000.0, 1024), (22050.0, 256), (192000.0, 2048)])
+def test_other_sample_rates_and_block_sizes(sr, block, jb, port):
+    """prepareToPlay(sampleRate, samplesPerBlock) at rates other than 48 kHz: every rate-dependent length (Width's 60 ms
+    ring, Texture's 80 ms waveguide, the analyzer's and Motion's cooldowns) and coefficient follows the reference."""
+    n_clips, n = 40, 3 * block + 64
+    for chain, settings in ((FULL_CHAIN, {}), (["JuicyPunch", "JuicyWidth"], {}), (["JuicyTexture"], {0: {"material": 2.0}}),
+                            (["JuicyTexture"], {0: {"material": 1.0}}), (["JuicyWidth", "JuicyInfer"], {0: {"haasMs": 17.0}})):
+        clips = jb.synth_clips("mixed", 5, n_clips, n, 2, sr)
+        eng = jb.BatchProcessor(chain, n_clips)
+        for slot, kv in settings.items():
+            for k, v in kv.items():
+                eng.setParameter(k, v, slot)
+        eng.prepareToPlay(sr, block)
+        out = eng.processBlock(clips)
+        recs = [eng.getLatestMetrics(s) for s in range(len(chain))]
+        eng.close()
+        for c in range(0, n_clips, 3):
+            ref, h = port.run_chain(chain, clips[c], sample_rate=sr, block_size=block, params=settings or None)
+            assert_samples_close(out[c], ref, "%s at %g Hz clip %d" % ("+".join(chain), sr, c))
+            for s in range(len(chain)):
+                assert_records_close(recs[s][c], h[s][-1], "%s at %g Hz clip %d slot %d" % ("+".join(chain), sr, c, s))
