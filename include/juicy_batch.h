@@ -86,7 +86,7 @@ int jb_device_count(void);
  * constructors' bus layout + setCurrentProgram(0) (:26-33).  `chain` holds
  * chain_len jb_plugin_kind values applied in order to every clip; n_channels is
  * the bus layout (isBusesLayoutSupported: mono or stereo in == out, e.g.
- * JuicyPunch/PluginProcessor.cpp:48-54; this build renders stereo only). */
+ * JuicyPunch/PluginProcessor.cpp:48-54): 1 or 2.  Mono audio is [clip][1][sample]. */
 int jb_create(const int* chain, int chain_len, int n_clips, int n_channels, int device, jb_engine** out);
 int jb_destroy(jb_engine* e);
 

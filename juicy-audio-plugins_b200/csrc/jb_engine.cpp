@@ -362,6 +362,10 @@ int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params
         }
         a.exactMath = e->mathMode == 1 || (e->mathMode == 0 && resonatorAfterShaper) ? 1 : 0;
     }
+    if (e->nCh == 1) { // mono buses run the generic kernel's one-channel instantiation: fast math, four samples per trip
+        a.exactMath = 0;
+        a.octets = 0;
+    }
     a.ana = jb::makeAnaCoef(e->sampleRate);
     for (size_t s = 0; s < e->chain.size(); ++s) {
         a.slot[s].kind = e->chain[s];
@@ -413,7 +417,7 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
 {
     // Path choice: the cooperative (time-parallel) kernel when the chain and the call's shape allow it and
     // the batch is too small to fill the GPU with one lane per clip; the lane-per-clip kernels otherwise.
-    bool coop = allowCoop && a.exactMath == 0 && e->coopCapable && e->dCoopScratch != nullptr && jbk_coop_supported(&a) != 0;
+    bool coop = allowCoop && a.exactMath == 0 && a.nCh == 2 && e->coopCapable && e->dCoopScratch != nullptr && jbk_coop_supported(&a) != 0;
     if (e->pathMode == 1)
         coop = false;
     else if (e->pathMode == 2 && !coop)
@@ -449,7 +453,7 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
     const char* splitEnv = std::getenv("JB_LANE_SPLIT");
     const bool splitChains = a.exactMath != 0 || splitEnv == nullptr || std::atoi(splitEnv) != 0;
     const int L = a.chainLen;
-    if (L > 1 && splitChains) {
+    if (L > 1 && splitChains && a.nCh == 2) {
         for (int s = 0; s < L; ++s) {
             ProcArgs one = a;
             one.in = s == 0 ? a.in : a.out;
@@ -731,8 +735,8 @@ int jb_create(const int* chain, int chain_len, int n_clips, int n_channels, int 
         return fail(JB_ERR_ARG, "jb_create: chain length %d outside 1..%d", chain_len, JB_MAX_CHAIN);
     if (n_clips < 1)
         return fail(JB_ERR_ARG, "jb_create: n_clips must be >= 1");
-    if (n_channels != 2)
-        return fail(JB_ERR_UNSUPPORTED, "jb_create: this build renders stereo buses only (n_channels = %d)", n_channels);
+    if (n_channels != 1 && n_channels != 2) // isBusesLayoutSupported: mono or stereo, in == out
+        return fail(JB_ERR_UNSUPPORTED, "jb_create: mono or stereo buses only (n_channels = %d)", n_channels);
     for (int i = 0; i < chain_len; ++i)
         if (chain[i] < 0 || chain[i] >= JB_NUM_KINDS)
             return fail(JB_ERR_ARG, "jb_create: unknown plugin kind %d at slot %d", chain[i], i);

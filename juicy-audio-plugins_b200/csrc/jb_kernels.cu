@@ -21,63 +21,6 @@ namespace {
 
 using namespace jbdev;
 
-template <class Main>
-__device__ __forceinline__ void sweep_pre_dispatch(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
-{
-    const int preSlot = mainSlot + 1;
-    if (preSlot >= a.chainLen) {
-        sweep<Main, PreNone>(a, clip, mainSlot, pos, n, blockAbs);
-        return;
-    }
-    switch (a.slot[preSlot].kind) {
-        case K_COHERE: sweep<Main, PreCohere>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_MOTION: sweep<Main, PreMotion>(a, clip, mainSlot, pos, n, blockAbs); break;
-        default: sweep<Main, PreAna>(a, clip, mainSlot, pos, n, blockAbs); break;
-    }
-}
-
-__device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
-{
-    if (mainSlot < 0) {
-        sweep_pre_dispatch<MainNone>(a, clip, mainSlot, pos, n, blockAbs);
-        return;
-    }
-    const SlotDesc& d = a.slot[mainSlot];
-    switch (d.kind) {
-        case K_INFER: sweep_pre_dispatch<MainInfer>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_PUNCH: sweep_pre_dispatch<MainPunch<false>>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_SAT: sweep_pre_dispatch<MainSat<false>>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_WIDTH: sweep_pre_dispatch<MainWidth>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_COHERE: sweep_pre_dispatch<MainCohere>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_MOTION: sweep_pre_dispatch<MainMotion>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_TEXTURE:
-            switch (d.c.tex.material) {
-                case 0: sweep_pre_dispatch<MainTexture<0>>(a, clip, mainSlot, pos, n, blockAbs); break;
-                case 1: sweep_pre_dispatch<MainTexture<1>>(a, clip, mainSlot, pos, n, blockAbs); break;
-                case 2: sweep_pre_dispatch<MainTexture<2>>(a, clip, mainSlot, pos, n, blockAbs); break;
-                case 3: sweep_pre_dispatch<MainTexture<3>>(a, clip, mainSlot, pos, n, blockAbs); break;
-                default: sweep_pre_dispatch<MainTexture<4>>(a, clip, mainSlot, pos, n, blockAbs); break;
-            }
-            break;
-        default: break;
-    }
-}
-
-
-__global__ void __launch_bounds__(JB_CTA_THREADS, 16) jb_process_kernel(const __grid_constant__ ProcArgs a)
-{
-    const long long lane = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= a.nClips)
-        return;
-    const long long clip = a.clipMap != nullptr ? (long long) a.clipMap[lane] : lane;
-    int blockAbs = a.histFirstBlock;
-    for (int pos = 0; pos < a.nSamples; pos += a.blockSize, ++blockAbs) {
-        const int n = min(a.blockSize, a.nSamples - pos);
-        for (int s = -1; s < a.chainLen; ++s)
-            sweep_dispatch(a, clip, s, pos, n, blockAbs);
-    }
-}
-
 __global__ void jb_fill_kernel(float* dst, float value, long long count)
 {
     const long long stride = (long long) gridDim.x * blockDim.x;
@@ -166,6 +109,7 @@ int check(cudaError_t e, const char* what)
 } // namespace
 
 extern "C" int jbk_launch_single(const ProcArgs* args, int grid, void* stream); // jb_single_light.cu
+extern "C" int jbk_launch_mono(const ProcArgs* args, int grid, void* stream);        // jb_mono.cu
 extern "C" int jbk_pair_supported(const ProcArgs* args);                          // jb_pair.cu
 extern "C" int jbk_launch_pair(const ProcArgs* args, void* stream);
 
@@ -182,6 +126,8 @@ int jbk_launch_process(const ProcArgs* args, void* stream)
     const int grid = (args->nClips + JB_CTA_THREADS - 1) / JB_CTA_THREADS;
     cudaStream_t st = (cudaStream_t) stream;
     ++g_launches;
+    if (args->nCh == 1) // mono bus: its own instantiation of the generic kernel (jb_mono.cu)
+        return check((cudaError_t) jbk_launch_mono(args, grid, stream), "jb_process_kernel<mono> launch");
     if (args->chainLen > 1 && args->exactMath)
         return check(cudaErrorInvalidValue, "exact math needs one launch per plugin (the fused kernel has the fast routines only)");
     if (args->chainLen == 1 && (!g_forceGeneric || args->exactMath)) {
@@ -196,7 +142,7 @@ int jbk_launch_process(const ProcArgs* args, void* stream)
         }
         return check((cudaError_t) jbk_launch_single(args, grid, stream), "jb_single_kernel launch");
     }
-    jb_process_kernel<<<grid, JB_CTA_THREADS, lane_smem_bytes(args->octets), st>>>(*args);
+    jb_process_kernel<false><<<grid, JB_CTA_THREADS, lane_smem_bytes(args->octets), st>>>(*args);
     return check(cudaGetLastError(), "jb_process_kernel launch");
 }
 

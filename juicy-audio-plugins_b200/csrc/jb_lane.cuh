@@ -171,6 +171,7 @@ struct AnaWalk {
 // must precede channel 1's), load/store of per-clip state, step(l, r) in place.
 
 struct MainBase {
+    static constexpr bool kMonoBypass = false; // the plugin returns before its DSP on a mono bus
     __device__ __forceinline__ void quad_begin() {} // around every group of four whole samples (vector path only)
     __device__ __forceinline__ void quad_end() {}
     __device__ __forceinline__ float stepCh0(float l) { return l; }
@@ -313,6 +314,7 @@ struct MainPunch : MainBase {
 // the delayed samples were written delaySamples ago -- so the ring's L2 / HBM latency no longer
 // sits in front of every sample (it was 55 % of all stall samples, profiles/r01_width_lane_*).
 struct MainWidth : MainBase {
+    static constexpr bool kMonoBypass = true; // JuicyWidth/PluginProcessor.cpp:76-89
     static constexpr bool kHas = true, kSeqChannels = false;
     static constexpr bool kHeavy = false; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     float width;
@@ -740,7 +742,7 @@ struct MainTexture : MainBase {
         ch0.store(L, b);
         ch1.store(L, b + TV_CH_STRIDE);
         L.sti(b + TV_WAVEIDX, waveIdx);
-        L.sti(b + TV_RNG, (int) rng1); // state after both channels' draws
+        L.sti(b + TV_RNG, (int) (L.a.nCh < 2 ? rng0 : rng1)); // state after both channels' draws (mono: channel 0's)
     }
 };
 
@@ -1051,14 +1053,18 @@ __device__ __forceinline__ void store8(float* p, const Quad& a, const Quad& b)
 }
 
 // One sweep over one block of one clip.  mainSlot < 0 for sweep 0.
-template <class Main, class Pre>
+// MONO: one-channel bus (isBusesLayoutSupported allows mono == mono, e.g. JuicyPunch/PluginProcessor.cpp:48-54).  The
+// reference then loops over one channel only, its analyzer reads the right sample as the left one
+// (src/shared/JuicinessAnalyzer.cpp:55-60), and Width does no DSP at all (JuicyWidth/PluginProcessor.cpp:76-89).  A
+// compile-time variant so that the stereo kernels' code is untouched; only the generic kernel is instantiated for it.
+template <class Main, class Pre, bool MONO = false>
 __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
 {
     const Lane L { a, clip };
     const int preSlot = mainSlot + 1;
     const bool firstRead = mainSlot <= 0; // sweep 0 and plugin 0's sweep read the caller's input
     const long long rowL = (clip * a.nCh) * a.rowPitch + pos;
-    const long long rowR = rowL + a.rowPitch;
+    const long long rowR = MONO ? rowL : rowL + a.rowPitch;
     const float* srcL = (firstRead ? a.in : a.out) + rowL;
     const float* srcR = (firstRead ? a.in : a.out) + rowR;
     float* dstL = a.out + rowL;
@@ -1075,6 +1081,8 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
         mainPart.load(L, a.slot[mainSlot], n);
         post.load(L, a.slot[mainSlot].stateBase);
         mustWrite = mainPart.writes(a.in != a.out);
+        if constexpr (MONO && Main::kMonoBypass)
+            mustWrite = a.in != a.out;
     }
     if constexpr (Pre::kHas) {
         pre.load(L, a.slot[preSlot].stateBase);
@@ -1097,13 +1105,17 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
     // per-sample bounds test, so the quad is ONE basic block and the scheduler can interleave the samples' and the two
     // channels' independent recurrences.
     auto quad_math = [&](Quad& ql, Quad& qr, int i, auto whole) {
-        if (vec)
+        constexpr bool kSkipMain = MONO && (Main::kMonoBypass || Main::kSeqChannels); // Width: no DSP; Motion: no channel 1
+        if (vec && !kSkipMain)
             mainPart.quad_begin();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (decltype(whole)::value || i + k < n) {
                 float l = ql.v[k], r = qr.v[k];
-                mainPart.step(l, r);
+                if constexpr (!kSkipMain)
+                    mainPart.step(l, r);
+                if constexpr (MONO)
+                    r = l; // `right != nullptr ? right[i] : l`
                 const float mono = 0.5f * (l + r);
                 stats.step(l, r, mono);
                 if constexpr (Main::kHas)
@@ -1116,7 +1128,7 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
                 qr.v[k] = r;
             }
         }
-        if (vec)
+        if (vec && !kSkipMain)
             mainPart.quad_end();
     };
     auto quad = [&](Quad& ql, Quad& qr, int i, auto whole) {
@@ -1124,7 +1136,8 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
         if (mustWrite) {
             if (!Main::kSeqChannels)
                 store4(dstL, i, n, vec, ql);
-            store4(dstR, i, n, vec, qr);
+            if constexpr (!MONO)
+                store4(dstR, i, n, vec, qr);
         }
     };
     constexpr std::true_type kWhole {};
@@ -1281,5 +1294,66 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
     }
 }
 
+
+// ------------------------------------------------------------------ generic multi-plugin kernel
+
+template <class Main, bool MONO>
+__device__ __forceinline__ void sweep_pre_dispatch(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
+{
+    const int preSlot = mainSlot + 1;
+    if (preSlot >= a.chainLen) {
+        sweep<Main, PreNone, MONO>(a, clip, mainSlot, pos, n, blockAbs);
+        return;
+    }
+    switch (a.slot[preSlot].kind) {
+        case K_COHERE: sweep<Main, PreCohere, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_MOTION: sweep<Main, PreMotion, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        default: sweep<Main, PreAna, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+    }
+}
+
+template <bool MONO>
+__device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
+{
+    if (mainSlot < 0) {
+        sweep_pre_dispatch<MainNone, MONO>(a, clip, mainSlot, pos, n, blockAbs);
+        return;
+    }
+    const SlotDesc& d = a.slot[mainSlot];
+    switch (d.kind) {
+        case K_INFER: sweep_pre_dispatch<MainInfer, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_PUNCH: sweep_pre_dispatch<MainPunch<false>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_SAT: sweep_pre_dispatch<MainSat<false>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_WIDTH: sweep_pre_dispatch<MainWidth, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_COHERE: sweep_pre_dispatch<MainCohere, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_MOTION: sweep_pre_dispatch<MainMotion, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_TEXTURE:
+            switch (d.c.tex.material) {
+                case 0: sweep_pre_dispatch<MainTexture<0>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+                case 1: sweep_pre_dispatch<MainTexture<1>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+                case 2: sweep_pre_dispatch<MainTexture<2>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+                case 3: sweep_pre_dispatch<MainTexture<3>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+                default: sweep_pre_dispatch<MainTexture<4>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+            }
+            break;
+        default: break;
+    }
+}
+
+
+template <bool MONO>
+__global__ void __launch_bounds__(JB_CTA_THREADS, 16) jb_process_kernel(const __grid_constant__ ProcArgs a)
+{
+    const long long lane = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= a.nClips)
+        return;
+    const long long clip = a.clipMap != nullptr ? (long long) a.clipMap[lane] : lane;
+    int blockAbs = a.histFirstBlock;
+    for (int pos = 0; pos < a.nSamples; pos += a.blockSize, ++blockAbs) {
+        const int n = min(a.blockSize, a.nSamples - pos);
+        for (int s = -1; s < a.chainLen; ++s)
+            sweep_dispatch<MONO>(a, clip, s, pos, n, blockAbs);
+    }
+}
 
 } // namespace

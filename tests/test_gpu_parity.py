@@ -444,3 +444,43 @@ def test_other_sample_rates_and_block_sizes(sr, block, jb, port):
             assert_samples_close(out[c], ref, "%s at %g Hz clip %d" % ("+".join(chain), sr, c))
             for s in range(len(chain)):
                 assert_records_close(recs[s][c], h[s][-1], "%s at %g Hz clip %d slot %d" % ("+".join(chain), sr, c, s))
+
+
+@pytest.mark.parametrize("chain", [[p] for p in PLUGINS] + [FULL_CHAIN], ids=list(PLUGINS) + ["full-chain"])
+def test_mono_bus_matches_oracle(chain, jb, port):
+    """One-channel buses (the reference's other supported layout): [clip][1][sample] audio, analyzer with right = left,
+    Width without DSP, Motion / Texture advancing their shared state for one channel only."""
+    n_clips, n = 37, 3 * BLOCK + 50
+    clips = jb.synth_clips("mixed", 3, n_clips, n, 1)
+    clips *= np.linspace(0.3, 1.7, n_clips, dtype=np.float32)[:, None, None]
+    settings = {chain.index("JuicyTexture"): {"material": 3.0}} if chain == ["JuicyTexture"] else {}
+    eng = jb.BatchProcessor(chain, n_clips, n_channels=1)
+    for slot, kv in settings.items():
+        for k, v in kv.items():
+            eng.setParameter(k, v, slot)
+    eng.set_math_mode("fast")
+    eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+    eng.enableHistory(8)
+    first = eng.processBlock(clips[:, :, :BLOCK + 10])          # ragged split: state carries across calls
+    second = eng.processBlock(clips[:, :, BLOCK + 10:])
+    recs = [eng.getLatestMetrics(s) for s in range(len(chain))]
+    eng.close()
+    for c in range(n_clips):
+        plugs = [port.PortPlugin(p, 1, SAMPLE_RATE, BLOCK) for p in chain]
+        for slot, kv in settings.items():
+            for k, v in kv.items():
+                plugs[slot].set_param(k, v)
+        for p in plugs:
+            p.prepare()
+        outs, last = [], None
+        for seg in (clips[c][:, :BLOCK + 10], clips[c][:, BLOCK + 10:]):
+            cur, last = seg, []
+            for p in plugs:
+                cur, h = p.process(cur)
+                last.append(h[-1])
+            outs.append(cur)
+        ref = np.concatenate(outs, axis=1)
+        got = np.concatenate([first[c], second[c]], axis=1)
+        assert_samples_close(got, ref, "%s mono clip %d" % ("+".join(chain), c))
+        for s in range(len(chain)):
+            assert_records_close(recs[s][c], last[s], "%s mono clip %d slot %d" % ("+".join(chain), c, s))

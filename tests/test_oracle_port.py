@@ -85,3 +85,30 @@ def test_port_programs_match_compiled_reference(plugin, port, refhost):
         b.set_program(i)
         assert a.program_name(i) == b.program_name(i)
         assert a.params() == b.params()
+
+
+@pytest.mark.parametrize("plugin", PLUGINS)
+def test_port_matches_compiled_reference_on_a_mono_bus(plugin, port, refhost):
+    """isBusesLayoutSupported allows mono == mono (e.g. JuicyPunch/PluginProcessor.cpp:48-54): one channel loop, the analyzer
+    reads right = left, Width returns before its DSP.  The port must follow the reference there too, bit for bit."""
+    if not refhost.available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this box and no prebuilt libraries)")
+    rng = np.random.default_rng(4321 + PLUGINS.index(plugin))
+    n = 3 * BLOCK + 77
+    x = (0.4 * rng.standard_normal((1, n))).astype(np.float32)
+    x[:, 700:760] *= 4.0
+    mats = range(5) if plugin == "JuicyTexture" else (None,)
+    for m in mats:
+        a = refhost.RefPlugin(plugin, 1, SAMPLE_RATE, BLOCK)
+        b = port.PortPlugin(plugin, 1, SAMPLE_RATE, BLOCK)
+        if m is not None:
+            a.set_param("material", float(m))
+            b.set_param("material", float(m))
+        a.prepare()
+        b.prepare()
+        oa, ha = a.process(x)
+        ob, hb = b.process(x)
+        assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32)), (plugin, m)
+        assert np.array_equal(ha.view(np.uint32), hb.view(np.uint32)), (plugin, m)
+        a.close()
+        b.close()
