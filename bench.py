@@ -250,6 +250,55 @@ def workload_config(args, n_clips_note=None):
 
 # ---------------------------------------------------------------------------------------------- engine arm
 
+FULL_CHAIN = ["JuicyPunch", "JuicySaturator", "JuicyTexture", "JuicyWidth", "JuicyMotion", "JuicyCohere", "JuicyInfer"]
+
+
+def survey_other_configs(jb, device, peak_gbs):
+    """Device-resident renders of BASELINE.json configs[0], [2], [3] and one 8-GPU shard of [4] (SURVEY.md §8(d) shapes),
+    timed with the library's CUDA events around its kernel launches; 1 warm-up + 2 timed renders each."""
+    specs = [
+        ("configs[0] C1: JuicySaturator, 1 clip x 10 s sine sweep", ["JuicySaturator"], 1, 480000, "sweep", None),
+        ("configs[2] C3: JuicyTexture, 8192 stereo instances (16384 streams), impulse trains, material = clip mod 5",
+         ["JuicyTexture"], 8192, 48000, "impulse", ("material", 5)),
+        ("configs[3] C4: JuicyInfer scoring, 65536 clips (noise / sweep / impulse / drum mix)", ["JuicyInfer"], 65536, 48000, "mixed", None),
+        ("configs[4] C5: full 7-plugin chain, one GPU's shard of 262144 clips (32768)", FULL_CHAIN, 32768, 48000, "mixed", None),
+    ]
+    out = []
+    for name, chain, n_clips, n, synth, clipmod in specs:
+        try:
+            buf = jb.DeviceBuffer(n_clips * 2 * n * 4, device)
+            jb.synth_fill_device(buf.ptr.value, synth, 0, n_clips, 2, n, SAMPLE_RATE, device=device, stream=0)
+            eng = jb.BatchProcessor(chain, n_clips, device=device)
+            if clipmod:
+                pid, k = clipmod
+                for c in range(n_clips):
+                    eng.setParameterClips(pid, float(c % k), c, 1, 0)
+            eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+            eng.reset()
+            eng.process_device(buf.ptr.value, buf.ptr.value, n)
+            eng.synchronize()
+            eng.kernel_time_ms()
+            steps = 2
+            for _ in range(steps):
+                eng.reset()
+                eng.process_device(buf.ptr.value, buf.ptr.value, n)
+            ms, launches = eng.kernel_time_ms()
+            ms /= steps
+            ch_samples = n_clips * 2 * n
+            read_only = chain == ["JuicyInfer"]
+            n_blocks = (n + BLOCK - 1) // BLOCK
+            alg = (4.0 if read_only else 8.0) * ch_samples + 64.0 * n_clips * n_blocks * len(chain)
+            out.append({"workload": name, "chain": chain, "clips": n_clips, "samples_per_clip": n, "ms_per_render": ms,
+                        "launches_per_render": launches / steps, "value": ch_samples / (ms / 1000.0), "unit": UNIT,
+                        "algorithmic_bytes": alg, "frac_of_hbm_peak": alg / (ms / 1000.0) / 1e9 / peak_gbs,
+                        "math": "exact (auto)" if chain == FULL_CHAIN else "fast (auto)"})
+            eng.close()
+            buf.free()
+        except Exception as exc:  # a survey line must never take the bench line down
+            out.append({"workload": name, "error": str(exc)})
+    return out
+
+
 def run_engine_arm(args):
     import torch
     import torch.distributed as dist
@@ -400,8 +449,18 @@ def run_engine_arm(args):
                 "value": 2 * cpu_clips * 2 * n / secs, "unit": UNIT, "cores": used, "kind": kind,
                 "sample": "%d of the %d drum-hit clips (x 2 ch x %d samples), 2 passes, %d host processes"
                           % (cpu_clips, n_clips, n, used)}
+        if world == 1 and not args.no_survey:
+            # the other BASELINE.json configurations, device resident, one GPU (explanatory: the bench line above is
+            # configs[1]); freed first: C4 alone holds 25 GB of input
+            eng.close()
+            del d_in, d_out, local_rec
+            torch.cuda.empty_cache()
+            line["other_configs"] = survey_other_configs(jb, local, peak)
         print(json.dumps(line))
-    eng.close()
+    try:
+        eng.close()
+    except Exception:
+        pass
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -417,6 +476,7 @@ def main():
     ap.add_argument("--samples", type=int, default=48000, help="samples per clip (1 s at 48 kHz)")
     ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU sample (default 4 per host thread)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-survey", action="store_true", help="skip the other_configs survey (N = 1 only)")
     ap.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_worker:
