@@ -131,6 +131,16 @@ int jb_schedule_param(jb_engine* e, int slot, const char* id, long long at_block
                       int n_clips);
 int jb_clear_schedule(jb_engine* e);
 
+/* State blobs: get/setStateInformation (e.g. JuicySaturator/PluginProcessor.cpp:117-131) -- the APVTS
+ * "PARAMS" tree (<PARAM id=".." value=".."/> per parameter) wrapped the way AudioProcessor::copyXmlToBinary does (magic
+ * 0x21324356, text length, single-line XML, NUL), so a state saved by the DAW plugin configures the batch engine and back.
+ * jb_get_state: clip = JB_ALL_CLIPS reads parameter set 0; buffer == NULL only reports the size.  jb_set_state: like
+ * replaceState -- every parameter takes the blob's value (through the same range handling as host automation), one the
+ * blob does not mention returns to its default; first_clip = JB_ALL_CLIPS applies to every clip.  JUCE itself is not
+ * available offline: the format follows its documentation (parity unpinned). */
+int jb_get_state(const jb_engine* e, int slot, int clip, void* buffer, size_t capacity, size_t* size_out);
+int jb_set_state(jb_engine* e, int slot, const void* data, size_t size, int first_clip, int n_clips);
+
 /* Programs: getNumPrograms / getCurrentProgram / setCurrentProgram / getProgramName
  * (e.g. JuicyWidth/PluginProcessor.cpp:171-210). */
 int jb_num_programs(const jb_engine* e, int slot);

@@ -994,6 +994,143 @@ int jb_clear_schedule(jb_engine* e)
     return JB_OK;
 }
 
+// ---------------------------------------------------------------- state blobs
+// get/setStateInformation (e.g. JuicySaturator/PluginProcessor.cpp:117-131): the APVTS state tree -- type "PARAMS", one
+// <PARAM id="..." value="..."/> child per parameter -- as the blob AudioProcessor::copyXmlToBinary makes of it: int32 LE magic
+// 0x21324356, int32 LE length of the XML text, the single-line UTF-8 XML text, one NUL.  JUCE is not available offline, so
+// this follows its documented format; the import side accepts any attribute order / whitespace / XML prolog.
+namespace {
+
+std::string formatStateValue(float v)
+{
+    char buf[64];
+    std::snprintf(buf, sizeof buf, "%.15g", (double) v);
+    std::string t(buf);
+    if (t.find_first_of(".eEn") == std::string::npos) // JUCE writes doubles with a decimal point ("6.0")
+        t += ".0";
+    return t;
+}
+
+std::string stateXml(const jb::ParamSet& p)
+{
+    const std::vector<jb::ParamSpec>& specs = jb::paramSpecs(p.kind());
+    std::string x = "<?xml version=\"1.0\" encoding=\"UTF-8\"?> <PARAMS>";
+    for (size_t i = 0; i < specs.size(); ++i)
+        x += std::string("<PARAM id=\"") + specs[i].id + "\" value=\"" + formatStateValue(p.raw((int) i)) + "\"/>";
+    x += "</PARAMS>";
+    return x;
+}
+
+// value of attribute `name` inside the tag text [b, e)
+bool xmlAttribute(const std::string& s, size_t b, size_t e, const char* name, std::string* out)
+{
+    const std::string key = std::string(name) + "=";
+    size_t pos = b;
+    while ((pos = s.find(key, pos)) != std::string::npos && pos < e) {
+        const bool boundary = pos == b || s[pos - 1] == ' ' || s[pos - 1] == '\t' || s[pos - 1] == '\n' || s[pos - 1] == '\r';
+        const size_t q = pos + key.size();
+        if (boundary && q < e && (s[q] == '"' || s[q] == '\'')) {
+            const size_t close = s.find(s[q], q + 1);
+            if (close == std::string::npos || close > e)
+                return false;
+            *out = s.substr(q + 1, close - q - 1);
+            return true;
+        }
+        pos = q;
+    }
+    return false;
+}
+
+// replaceState(ValueTree::fromXml(...)): every parameter takes its child's value; one without a child goes back to its
+// default (AudioProcessorValueTreeState re-creates the missing child from the parameter's default value)
+int applyStateXml(const std::string& xml, jb::ParamSet& p)
+{
+    const size_t root = xml.find("<PARAMS");
+    if (root == std::string::npos)
+        return JB_ERR_ARG; // setStateInformation ignores trees of another type; the C ABI reports it
+    const std::vector<jb::ParamSpec>& specs = jb::paramSpecs(p.kind());
+    std::vector<char> seen(specs.size(), 0);
+    size_t pos = root;
+    while ((pos = xml.find("<PARAM", pos + 1)) != std::string::npos) {
+        const char after = pos + 6 < xml.size() ? xml[pos + 6] : '>';
+        if (after != ' ' && after != '\t' && after != '\n' && after != '\r' && after != '/')
+            continue; // <PARAMS ...>
+        const size_t end = xml.find('>', pos);
+        if (end == std::string::npos)
+            break;
+        std::string id, value;
+        if (!xmlAttribute(xml, pos, end, "id", &id) || !xmlAttribute(xml, pos, end, "value", &value))
+            continue;
+        const int idx = p.find(id.c_str());
+        if (idx < 0)
+            continue;
+        char* stop = nullptr;
+        const double v = std::strtod(value.c_str(), &stop);
+        if (stop == value.c_str())
+            continue;
+        p.setPlain(idx, (float) v);
+        seen[(size_t) idx] = 1;
+    }
+    for (size_t i = 0; i < specs.size(); ++i)
+        if (!seen[i])
+            p.setPlain((int) i, specs[i].def);
+    return JB_OK;
+}
+
+} // namespace
+
+int jb_get_state(const jb_engine* e, int slot, int clip, void* buffer, size_t capacity, size_t* size_out)
+{
+    if (int rc = checkSlot(e, slot))
+        return rc;
+    if (clip != JB_ALL_CLIPS && (clip < 0 || clip >= e->nClips))
+        return fail(JB_ERR_ARG, "jb_get_state: clip %d outside the engine's %d clips", clip, e->nClips);
+    const int set = clip == JB_ALL_CLIPS || e->clipSet.empty() ? 0 : e->clipSet[(size_t) clip];
+    const std::string xml = stateXml(paramsOfSet(e, set)[(size_t) slot]);
+    const size_t total = 8 + xml.size() + 1;
+    if (size_out != nullptr)
+        *size_out = total;
+    if (buffer == nullptr)
+        return JB_OK; // size query
+    if (capacity < total)
+        return fail(JB_ERR_ARG, "jb_get_state: buffer of %zu bytes, %zu needed", capacity, total);
+    unsigned char* out = static_cast<unsigned char*>(buffer);
+    const uint32_t magic = 0x21324356u, len = (uint32_t) xml.size();
+    for (int i = 0; i < 4; ++i) {
+        out[i] = (unsigned char) (magic >> (8 * i));
+        out[4 + i] = (unsigned char) (len >> (8 * i));
+    }
+    std::memcpy(out + 8, xml.data(), xml.size());
+    out[8 + xml.size()] = 0;
+    return JB_OK;
+}
+
+int jb_set_state(jb_engine* e, int slot, const void* data, size_t size, int first_clip, int n_clips)
+{
+    if (int rc = checkSlot(e, slot))
+        return rc;
+    if (int rc = checkClipRange(e, first_clip, n_clips))
+        return rc;
+    if (data == nullptr || size < 9)
+        return fail(JB_ERR_ARG, "jb_set_state: no state blob");
+    const unsigned char* in = static_cast<const unsigned char*>(data);
+    uint32_t magic = 0, len = 0;
+    for (int i = 0; i < 4; ++i) {
+        magic |= (uint32_t) in[i] << (8 * i);
+        len |= (uint32_t) in[4 + i] << (8 * i);
+    }
+    if (magic != 0x21324356u) // getXmlFromBinary returns nullptr and setStateInformation does nothing
+        return fail(JB_ERR_ARG, "jb_set_state: not a copyXmlToBinary blob (magic %08x)", magic);
+    const size_t textLen = std::min<size_t>(len, size - 8);
+    const std::string xml(reinterpret_cast<const char*>(in + 8), textLen);
+    jb::ParamSet probe = e->params[(size_t) slot];
+    if (applyStateXml(xml, probe) != JB_OK)
+        return fail(JB_ERR_ARG, "jb_set_state: the blob holds no <PARAMS> tree");
+    changeParams(e, first_clip == JB_ALL_CLIPS ? 0 : first_clip, first_clip == JB_ALL_CLIPS ? -1 : n_clips,
+                 [&](std::vector<jb::ParamSet>& p) { applyStateXml(xml, p[(size_t) slot]); });
+    return JB_OK;
+}
+
 int jb_num_programs(const jb_engine* e, int slot) { return checkSlot(e, slot) == JB_OK ? e->params[(size_t) slot].numPrograms() : JB_ERR_ARG; }
 int jb_get_program(const jb_engine* e, int slot) { return checkSlot(e, slot) == JB_OK ? e->params[(size_t) slot].currentProgram() : JB_ERR_ARG; }
 

@@ -138,6 +138,19 @@ public:
         check(jb_schedule_param(e_, slot, id, atBlock, plain, firstClip, nClips));
     }
     void setMathMode(int mode) { check(jb_set_math_mode(e_, mode)); }
+    // get/setStateInformation: the copyXmlToBinary blob of the APVTS "PARAMS" tree
+    std::vector<unsigned char> getStateInformation(int slot, int clip = JB_ALL_CLIPS) const
+    {
+        size_t size = 0;
+        check(jb_get_state(e_, slot, clip, nullptr, 0, &size));
+        std::vector<unsigned char> blob(size);
+        check(jb_get_state(e_, slot, clip, blob.data(), blob.size(), &size));
+        return blob;
+    }
+    void setStateInformation(int slot, const void* data, size_t size, int firstClip = JB_ALL_CLIPS, int nClips = 0)
+    {
+        check(jb_set_state(e_, slot, data, size, firstClip, nClips));
+    }
 
     // JuicyMeterPanel state of every clip after the render (src/shared/JuicyMeterPanel.cpp:9-34,54-71)
     std::vector<jb_meter_stats> getMeterStatistics(int slot, int firstBlock, int nBlocks, int blockStride = 1)

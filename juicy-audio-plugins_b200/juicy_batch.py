@@ -73,6 +73,8 @@ def lib():
         "jb_num_param_sets": (ci, [vp]),
         "jb_schedule_param": (ci, [vp, ci, ctypes.c_char_p, cll, ctypes.c_float, ci, ci]),
         "jb_clear_schedule": (ci, [vp]),
+        "jb_get_state": (ci, [vp, ci, ci, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+        "jb_set_state": (ci, [vp, ci, vp, ctypes.c_size_t, ci, ci]),
         "jb_num_programs": (ci, [vp, ci]),
         "jb_get_program": (ci, [vp, ci]),
         "jb_set_program": (ci, [vp, ci, ci]),
@@ -298,6 +300,18 @@ class BatchProcessor:
 
     def clearSchedule(self):
         _check(lib().jb_clear_schedule(self._h))
+
+    # ---- state blobs (get/setStateInformation)
+    def getStateInformation(self, slot=0, clip=-1):
+        size = ctypes.c_size_t()
+        _check(lib().jb_get_state(self._h, self.slot(slot), int(clip), None, 0, ctypes.byref(size)))
+        buf = ctypes.create_string_buffer(size.value)
+        _check(lib().jb_get_state(self._h, self.slot(slot), int(clip), buf, size.value, ctypes.byref(size)))
+        return buf.raw[:size.value]
+
+    def setStateInformation(self, blob, slot=0, first_clip=-1, n_clips=0):
+        data = bytes(blob)
+        _check(lib().jb_set_state(self._h, self.slot(slot), data, len(data), int(first_clip), int(n_clips)))
 
     def getNumPrograms(self, slot=0):
         return lib().jb_num_programs(self._h, self.slot(slot))
