@@ -291,7 +291,7 @@ def survey_other_configs(jb, device, peak_gbs):
             out.append({"workload": name, "chain": chain, "clips": n_clips, "samples_per_clip": n, "ms_per_render": ms,
                         "launches_per_render": launches / steps, "value": ch_samples / (ms / 1000.0), "unit": UNIT,
                         "algorithmic_bytes": alg, "frac_of_hbm_peak": alg / (ms / 1000.0) / 1e9 / peak_gbs,
-                        "math": "exact (auto)" if chain == FULL_CHAIN else "fast (auto)"})
+                        "math": "auto (fast: no resonant Texture material behind a shaper in these configurations)"})
             eng.close()
             buf.free()
         except Exception as exc:  # a survey line must never take the bench line down

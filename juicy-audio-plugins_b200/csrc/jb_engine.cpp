@@ -353,12 +353,20 @@ int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params
     {   // Saturator / Punch transcendentals: the MUFU-based ones are within 3e-6 of the reference, which Texture's metal /
         // wood / plastic resonators amplify ~200x; with a Texture further down the chain they run the C library's own
         // algorithms (jb_libm.h) so that its input is the reference's, bit for bit.
+        // Which materials: measured on the full chain (profiles/r01_s6_chain_sensitivity.txt) gel and flesh stay at 1e-6 of
+        // clip peak with the fast routines (their mass-spring models are heavily damped), metal / wood / plastic reach
+        // 4e-5 .. 4e-3 -- so only a Texture whose material is one of those three asks for the exact routines.  Decided per
+        // launch from the parameter set being rendered (per-clip sets and automation each get their own answer).
         bool shaperSeen = false, resonatorAfterShaper = false;
-        for (int k : e->chain) {
+        for (size_t s2 = 0; s2 < e->chain.size(); ++s2) {
+            const int k = e->chain[s2];
             if (k == jb::kPunch || k == jb::kSaturator)
                 shaperSeen = true;
-            if (k == jb::kTexture && shaperSeen)
-                resonatorAfterShaper = true;
+            if (k == jb::kTexture && shaperSeen) {
+                const int material = (int) params[s2].raw("material");
+                if (material >= 1 && material <= 3)
+                    resonatorAfterShaper = true;
+            }
         }
         a.exactMath = e->mathMode == 1 || (e->mathMode == 0 && resonatorAfterShaper) ? 1 : 0;
     }
