@@ -290,10 +290,39 @@ struct MainPunch : MainBase {
         wet = soft + c.clipAmt * (hard - soft);
         return (dry + c.mix * (wet - dry)) * c.outGain;
     }
+    // both channels in packed halves: the operations of one() in the same order (see MainCohere::step)
     __device__ __forceinline__ void step(float& l, float& r)
     {
-        l = one(l, f0, sl0);
-        r = one(r, f1, sl1);
+        const F2 dry = f2(l, r);
+        const F2 adry = f2(fabsf(l), fabsf(r));
+        const F2 fin = mul2(f2(c.omFast), adry), fkeep = mul2(f2(c.fastCoeff), f2(f0, f1));
+        const F2 sin_ = mul2(f2(c.omSlow), adry), skeep = mul2(f2(c.slowCoeff), f2(sl0, sl1));
+        f0 = fin.x + fkeep.x;
+        f1 = fin.y + fkeep.y;
+        sl0 = sin_.x + skeep.x;
+        sl1 = sin_.y + skeep.y;
+        const F2 S = f2(sl0, sl1);
+        const F2 d = sub2(f2(f0, f1), S);
+        const F2 tr = f2(jmaxf(0.0f, d.x), jmaxf(0.0f, d.y));
+        const F2 curve = EXACT ? f2(jblibm::powf_glibc_pos(tr.x, c.curveExp), jblibm::powf_glibc_pos(tr.y, c.curveExp))
+                               : f2(pow_unit(tr.x, c.curveExp), pow_unit(tr.y, c.curveExp));
+        const F2 punchGain = mul_add2(f2(c.punchK), curve, f2(1.0f));
+        const F2 t06 = mul2(tr, f2(0.6f));
+        const F2 sus = f2(jmaxf(0.0f, S.x - t06.x), jmaxf(0.0f, S.y - t06.y));
+        const F2 sustainGain = mul_add2(f2(c.sustainK), sus, f2(1.0f));
+        const F2 wet0 = mul2(mul2(dry, punchGain), sustainGain);
+        const F2 driven = mul2(wet0, f2(c.drive));
+        F2 soft;
+        if (EXACT)
+            soft = f2(jblibm::fdiv(jblibm::tanhf_fdlibm(driven.x), c.tanhDrive), jblibm::fdiv(jblibm::tanhf_fdlibm(driven.y), c.tanhDrive));
+        else
+            soft = mul2(tanh_fast2(driven), f2(invTanhDrive));
+        const F2 hk = mul2(wet0, f2(c.hardK));
+        const F2 hard = f2(jlimitf(-0.95f, 0.95f, hk.x), jlimitf(-0.95f, 0.95f, hk.y));
+        const F2 wet = mul_add2(f2(c.clipAmt), f2(hard.x - soft.x, hard.y - soft.y), soft);
+        const F2 out = mul2(mul_add2(f2(c.mix), sub2(wet, dry), dry), f2(c.outGain));
+        l = out.x;
+        r = out.y;
     }
     __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
     {
@@ -426,10 +455,25 @@ struct MainCohere : MainBase {
         const float wet = matched + c.tailK * tail;
         return (dry + c.mix * (wet - dry)) * c.outGain;
     }
+    // both channels in packed halves: the operations of one() in the same order (adds that consume a packed product stay
+    // scalar, see the caution at F2 in jb_device.cuh)
     __device__ __forceinline__ void step(float& l, float& r)
     {
-        l = one(l, a0, b0, t0);
-        r = one(r, a1, b1, t1);
+        const F2 dry = f2(l, r);
+        F2 A = f2(a0, a1), B = f2(b0, b1), T = f2(t0, t1);
+        A = mul_add2(f2(c.lowCoeff), sub2(dry, A), A);
+        B = mul_add2(f2(c.highCoeff), sub2(dry, B), B);
+        const F2 low = mul2(A, f2(lowComp));
+        const F2 hb = sub2(dry, B);
+        const F2 high = mul2(hb, f2(highComp));
+        const F2 mid = mul2(sub2(sub2(dry, A), hb), f2(midComp));
+        const F2 matched = f2((low.x + mid.x) + high.x, (low.y + mid.y) + high.y);
+        T = mul_add2(T, f2(c.fb), matched);
+        const F2 wet = mul_add2(f2(c.tailK), T, matched);
+        const F2 out = mul2(mul_add2(f2(c.mix), sub2(wet, dry), dry), f2(c.outGain));
+        a0 = A.x; a1 = A.y; b0 = B.x; b1 = B.y; t0 = T.x; t1 = T.y;
+        l = out.x;
+        r = out.y;
     }
     __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)
     {
