@@ -304,10 +304,10 @@ int resetState(jb_engine* e)
 // streaming (jb_lane.cuh).  Measured (profiles/r01_s6_tile.txt): the tile wins where nothing is written back -- Infer,
 // 16384 clips 7.0 -> 5.6 ms, 65536 clips out of place 19.3 -> 16.5 ms -- and loses for the plugins that store every sample
 // (Saturator 65536 clips 20.0 -> 23.8 ms), so only Infer takes it.  JB_TILE=0 / 1 forces it off / on for light plugins.
-int octetsFor(int kind, int nClips, int nSamples, bool mapped)
+int octetsFor(int kind, int nClips, int nSamples, bool mapped, bool exactMath)
 {
     static const int tileMode = [] { const char* v = std::getenv("JB_TILE"); return v == nullptr ? -1 : std::atoi(v); }();
-    if (mapped || kind == jb::kPunch || kind == jb::kTexture || kind == jb::kMotion)
+    if (mapped || kind == jb::kTexture || kind == jb::kMotion || (kind == jb::kPunch && exactMath))
         return 0;
     const bool tileOk = nClips % 32 == 0 && nSamples % 4 == 0;
     const bool tile = tileMode < 0 ? (kind == jb::kInfer && nClips >= 8192) : tileMode != 0;
@@ -343,7 +343,7 @@ int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params
     const bool aligned = ((reinterpret_cast<uintptr_t>(dIn) | reinterpret_cast<uintptr_t>(dOut)) & 15u) == 0;
     a.vecOk = (aligned && nSamples % 4 == 0 && a.rowPitch % 4 == 0 && e->blockSize % 4 == 0) ? 1 : 0;
     a.lightOctets = 0; // per launch, see octetsFor()
-    a.octets = e->chain.size() == 1 ? octetsFor(e->chain[0], nClips, nSamples, false) : 0;
+    a.octets = 0; // single-plugin engines: set below, once the math mode of this launch is known
     if (e->chain.size() > 1) { // fused generic kernel: eight samples per trip only when every plugin is light
         a.octets = nClips >= 32768 ? 1 : 0;
         for (int k : e->chain)
@@ -370,6 +370,8 @@ int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params
         }
         a.exactMath = e->mathMode == 1 || (e->mathMode == 0 && resonatorAfterShaper) ? 1 : 0;
     }
+    if (e->chain.size() == 1)
+        a.octets = octetsFor(e->chain[0], nClips, nSamples, false, a.exactMath != 0);
     if (e->nCh == 1) { // mono buses run the generic kernel's one-channel instantiation: fast math, four samples per trip
         a.exactMath = 0;
         a.octets = 0;
@@ -469,7 +471,7 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
             one.slot[0] = a.slot[s];
             one.recSlotBase = s;
             one.recChainLen = L;
-            one.octets = octetsFor(one.slot[0].kind, a.nClips, a.nSamples, a.clipMap != nullptr);
+            one.octets = octetsFor(one.slot[0].kind, a.nClips, a.nSamples, a.clipMap != nullptr, a.exactMath != 0);
             if (jbk_launch_process(&one, stream) != 0)
                 return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
         }

@@ -260,7 +260,7 @@ struct MainSat : MainBase {
 template <bool EXACT>
 struct MainPunch : MainBase {
     static constexpr bool kHas = true, kSeqChannels = false;
-    static constexpr bool kHeavy = true; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
+    static constexpr bool kHeavy = EXACT; // heavy per-sample state: 4 samples per trip (registers); light: 8 (one sector per store)
     float f0, f1, sl0, sl1, invTanhDrive;
     PunchCoef c;
     __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int)
