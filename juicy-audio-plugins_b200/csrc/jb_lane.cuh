@@ -1134,13 +1134,15 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
     }
 
     if constexpr (Main::kSeqChannels) { // Motion: channel 0's block first
+        Quad q = load4(srcL, 0, n, vec);
         for (int i = 0; i < n; i += 4) {
-            Quad q = load4(srcL, i, n, vec);
+            const Quad next = i + 4 < n ? load4(srcL, i + 4, n, vec) : q; // one quad ahead: its L2 latency hides behind this one
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (i + k < n)
                     q.v[k] = mainPart.stepCh0(q.v[k]);
             store4(dstL, i, n, vec, q);
+            q = next;
         }
         srcL = dstL;
     }
