@@ -193,6 +193,23 @@ typedef struct jb_meter_stats {
 } jb_meter_stats;
 int jb_meter_statistics(jb_engine* e, int slot, int first_block, int n_blocks, int block_stride, jb_meter_stats* out);
 
+/* Audio files.  The reference never touches files -- its DAW host decodes them into the fp32
+ * AudioBuffers processBlock receives -- so an offline batch renderer does that step itself: RIFF/WAVE, PCM 16 / 24 / 32-bit
+ * integer or 32-bit float, plain or WAVE_FORMAT_EXTENSIBLE header, to / from planar [channel][sample] fp32 host buffers
+ * (one clip of jb_process_host's layout).  Integer samples convert like JUCE's WavAudioFormat: value / 2^(bits-1) on
+ * reading, round(value * 2^(bits-1)) limited to +-(2^(bits-1) - 1) on writing.  Host code only (works without a GPU).
+ * Errors: JB_ERR_ARG with a message in jb_wav_last_error(). */
+typedef struct jb_wav_info {
+    int n_channels, n_samples;
+    double sample_rate;
+    int bits_per_sample, is_float;
+} jb_wav_info;
+const char* jb_wav_last_error(void);
+int jb_wav_info_read(const char* path, jb_wav_info* out);
+int jb_wav_read(const char* path, float* h_planar, int n_channels, int n_samples);
+int jb_wav_write(const char* path, const float* h_planar, int n_channels, int n_samples, double sample_rate,
+                 int bits_per_sample, int is_float);
+
 /* Seeded synthetic clips written straight into device memory:
  * kind 0 sweep, 1 noise, 2 impulse train, 3 drum hit, 4 mixed (clip mod 4).
  * first_clip offsets the per-clip seeds so shards of one job stay distinct. */

@@ -75,6 +75,10 @@ def lib():
         "jb_clear_schedule": (ci, [vp]),
         "jb_get_state": (ci, [vp, ci, ci, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
         "jb_set_state": (ci, [vp, ci, vp, ctypes.c_size_t, ci, ci]),
+        "jb_wav_last_error": (ctypes.c_char_p, []),
+        "jb_wav_info_read": (ci, [ctypes.c_char_p, vp]),
+        "jb_wav_read": (ci, [ctypes.c_char_p, vp, ci, ci]),
+        "jb_wav_write": (ci, [ctypes.c_char_p, vp, ci, ci, cd, ci, ci]),
         "jb_num_programs": (ci, [vp, ci]),
         "jb_get_program": (ci, [vp, ci]),
         "jb_set_program": (ci, [vp, ci, ci]),
@@ -407,6 +411,38 @@ def synth_fill_device(d_ptr, kind, first_clip, n_clips, n_channels, n_samples, s
     k = SYNTH_KINDS[kind] if isinstance(kind, str) else int(kind)
     _check(lib().jb_synth_fill(ctypes.c_void_p(int(d_ptr)), k, int(first_clip), int(n_clips), int(n_channels), int(n_samples),
                                float(sample_rate), ctypes.c_uint(seed), int(device), ctypes.c_void_p(int(stream))))
+
+
+class WavInfo(ctypes.Structure):
+    _fields_ = [("n_channels", ctypes.c_int), ("n_samples", ctypes.c_int), ("sample_rate", ctypes.c_double),
+                ("bits_per_sample", ctypes.c_int), ("is_float", ctypes.c_int)]
+
+
+def _check_wav(rc):
+    if rc != JB_OK:
+        raise JuicyBatchError(rc, lib().jb_wav_last_error().decode("utf-8", "replace"))
+
+
+def wav_info(path):
+    info = WavInfo()
+    _check_wav(lib().jb_wav_info_read(os.fsencode(path), ctypes.byref(info)))
+    return {"n_channels": info.n_channels, "n_samples": info.n_samples, "sample_rate": info.sample_rate,
+            "bits_per_sample": info.bits_per_sample, "is_float": bool(info.is_float)}
+
+
+def wav_read(path):
+    """(float32 [n_channels][n_samples], sample_rate) of a RIFF/WAVE file (PCM 16/24/32 or float32)."""
+    info = wav_info(path)
+    out = np.zeros((info["n_channels"], info["n_samples"]), dtype=np.float32)
+    _check_wav(lib().jb_wav_read(os.fsencode(path), out.ctypes.data, info["n_channels"], info["n_samples"]))
+    return out, info["sample_rate"]
+
+
+def wav_write(path, audio, sample_rate=48000.0, bits_per_sample=24, is_float=False):
+    a = np.ascontiguousarray(audio, dtype=np.float32)
+    assert a.ndim == 2
+    _check_wav(lib().jb_wav_write(os.fsencode(path), a.ctypes.data, a.shape[0], a.shape[1], float(sample_rate),
+                                  int(bits_per_sample), int(bool(is_float))))
 
 
 def synth_clips(kind, first_clip, n_clips, n_samples, n_channels=2, sample_rate=48000.0, seed=0x4A554943):
