@@ -131,6 +131,8 @@ struct jb_engine {
     cudaStream_t groupStream[kGroupStreams] = {};
     cudaEvent_t groupJoin[kGroupStreams] = {};
     cudaEvent_t groupFork = nullptr;
+    std::vector<cudaEvent_t> pipeEvents; // [plugin][segment] of a pipelined chain render
+    int pipelineMaxClips = 16384;        // chains of at most this many clips are pipelined across plugins
 
     // CUDA-event pairs around every render-kernel launch (jb_kernel_time_ms)
     std::vector<cudaEvent_t> timingEvents; // start0, stop0, start1, stop1, ...
@@ -186,6 +188,9 @@ void freeDevice(jb_engine* e)
     }
     if (e->groupFork) cudaEventDestroy(e->groupFork);
     e->groupFork = nullptr;
+    for (cudaEvent_t ev : e->pipeEvents)
+        cudaEventDestroy(ev);
+    e->pipeEvents.clear();
     e->groupsDirty = true;
     e->dState = e->dLatest = e->dHist = e->dRing = e->dWave = e->dCoopScratch = nullptr;
     for (int i = 0; i < 3; ++i) {
@@ -421,6 +426,19 @@ int timingPair(jb_engine* e, cudaEvent_t* start, cudaEvent_t* stop)
     return JB_OK;
 }
 
+// Side streams for launches that may overlap (parameter sets of one call; the plugins of a pipelined chain)
+int ensureGroupStreams(jb_engine* e)
+{
+    if (e->groupStream[0] != nullptr)
+        return JB_OK;
+    for (int i = 0; i < jb_engine::kGroupStreams; ++i) {
+        JB_CUDA(cudaStreamCreateWithFlags(&e->groupStream[i], cudaStreamNonBlocking));
+        JB_CUDA(cudaEventCreateWithFlags(&e->groupJoin[i], cudaEventDisableTiming));
+    }
+    JB_CUDA(cudaEventCreateWithFlags(&e->groupFork, cudaEventDisableTiming));
+    return JB_OK;
+}
+
 // The render kernel(s) of one ProcArgs on `stream`, untimed.  allowCoop: the cooperative kernel may be chosen (it owns
 // engine-wide scratch, so concurrent launches of several parameter sets stay on the lane kernels).
 int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool allowCoop)
@@ -464,16 +482,68 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
     const bool splitChains = a.exactMath != 0 || splitEnv == nullptr || std::atoi(splitEnv) != 0;
     const int L = a.chainLen;
     if (L > 1 && splitChains && a.nCh == 2) {
-        for (int s = 0; s < L; ++s) {
+        auto launchOne = [&](int s, int t0, int ns, int firstBlock, cudaStream_t st) -> int {
             ProcArgs one = a;
-            one.in = s == 0 ? a.in : a.out;
+            one.in = (s == 0 ? a.in : a.out) + t0;
+            one.out = a.out + t0;
+            one.nSamples = ns;
+            one.histFirstBlock = a.histFirstBlock + firstBlock;
             one.chainLen = 1;
             one.slot[0] = a.slot[s];
             one.recSlotBase = s;
             one.recChainLen = L;
-            one.octets = octetsFor(one.slot[0].kind, a.nClips, a.nSamples, a.clipMap != nullptr, a.exactMath != 0);
-            if (jbk_launch_process(&one, stream) != 0)
+            one.octets = octetsFor(one.slot[0].kind, a.nClips, ns, a.clipMap != nullptr, a.exactMath != 0);
+            if (jbk_launch_process(&one, st) != 0)
                 return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
+            return JB_OK;
+        };
+        // Plugin pipeline across streams.  One launch per plugin over the whole call leaves a small batch's GPU mostly
+        // idle: each launch is a latency-bound walk through time on a few hundred warps, and the L launches run one
+        // after the other.  Cut the call into segments of whole host blocks instead and give every plugin its own
+        // stream: plugin s renders segment k as soon as plugin s - 1 has (an event) and it has finished segment k - 1
+        // itself (stream order), so up to L kernels run side by side on different stretches of time -- the same
+        // arithmetic in the same order per clip, state carried across launches as between host callbacks.
+        // Measured: profiles/r01_s6_pipeline.txt.  JB_CHAIN_PIPELINE=0 / 1 forces it off / on.
+        static const int pipeMode = [] { const char* v = std::getenv("JB_CHAIN_PIPELINE"); return v == nullptr ? -1 : std::atoi(v); }();
+        const int B = a.blockSize;
+        const int nBlocks = (a.nSamples + B - 1) / B;
+        const bool onEngineStream = stream == e->stream && L <= jb_engine::kGroupStreams;
+        const bool pipeline = onEngineStream && nBlocks >= 4 && (pipeMode < 0 ? a.nClips <= e->pipelineMaxClips : pipeMode != 0);
+        if (!pipeline) {
+            for (int s = 0; s < L; ++s)
+                if (int rc = launchOne(s, 0, a.nSamples, 0, stream))
+                    return rc;
+        } else {
+            static const int segEnv = [] { const char* v = std::getenv("JB_PIPE_SEGMENTS"); return v == nullptr ? 32 : std::max(2, std::atoi(v)); }();
+            const int K = std::min(segEnv, nBlocks / 2);
+            const int segBlocks = (nBlocks + K - 1) / K;
+            if (int rc = ensureGroupStreams(e))
+                return rc;
+            while (e->pipeEvents.size() < (size_t) L * (size_t) K) {
+                cudaEvent_t ev = nullptr;
+                JB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                e->pipeEvents.push_back(ev);
+            }
+            JB_CUDA(cudaEventRecord(e->groupFork, stream));
+            for (int s = 0; s < L; ++s)
+                JB_CUDA(cudaStreamWaitEvent(e->groupStream[s], e->groupFork, 0));
+            for (int k = 0; k * segBlocks < nBlocks; ++k) {
+                const int b0 = k * segBlocks;
+                const int t0 = b0 * B;
+                const int ns = std::min(a.nSamples - t0, segBlocks * B);
+                for (int s = 0; s < L; ++s) {
+                    cudaStream_t st = e->groupStream[s];
+                    if (s > 0)
+                        JB_CUDA(cudaStreamWaitEvent(st, e->pipeEvents[(size_t) (s - 1) * K + k], 0));
+                    if (int rc = launchOne(s, t0, ns, b0, st))
+                        return rc;
+                    JB_CUDA(cudaEventRecord(e->pipeEvents[(size_t) s * K + k], st));
+                }
+            }
+            for (int s = 0; s < L; ++s) {
+                JB_CUDA(cudaEventRecord(e->groupJoin[s], e->groupStream[s]));
+                JB_CUDA(cudaStreamWaitEvent(stream, e->groupJoin[s], 0));
+            }
         }
     } else if (jbk_launch_process(&a, stream) != 0) {
         return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
@@ -615,13 +685,8 @@ int renderClips(jb_engine* e, const float* dIn, float* dOut, int ns, int nc, lon
     // through time), so they go out on a small pool of side streams between a fork and a join on the engine's stream.
     const long long clipStride = (long long) e->nCh * rowPitch;
     constexpr int kPool = jb_engine::kGroupStreams;
-    if (e->groupStream[0] == nullptr) {
-        for (int i = 0; i < kPool; ++i) {
-            JB_CUDA(cudaStreamCreateWithFlags(&e->groupStream[i], cudaStreamNonBlocking));
-            JB_CUDA(cudaEventCreateWithFlags(&e->groupJoin[i], cudaEventDisableTiming));
-        }
-        JB_CUDA(cudaEventCreateWithFlags(&e->groupFork, cudaEventDisableTiming));
-    }
+    if (int rc = ensureGroupStreams(e))
+        return rc;
     static const bool forceSerial = [] { const char* v = std::getenv("JB_GROUP_SERIAL"); return v != nullptr && std::atoi(v) != 0; }();
     // ... as long as all of them fit the GPU together (the heavy kernels hold at most 8 warps per SM): beyond that the
     // launches queue behind each other's tails and one after the other is faster (32768 clips in 5 Texture materials:

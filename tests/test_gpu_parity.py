@@ -347,7 +347,7 @@ eng = jb.BatchProcessor(chain, %d)
 for slot, pid, v in %r:
     eng.setParameter(pid, v, slot)
 eng.set_path("lane"); eng.set_math_mode(%r)
-eng.prepareToPlay(48000.0, 512); eng.enableHistory(16)
+eng.prepareToPlay(48000.0, 512); eng.enableHistory(64)
 a = eng.processBlock(clips[:, :, :1024]); b = eng.processBlock(clips[:, :, 1024:])
 np.savez(sys.argv[1], out=np.concatenate([a, b], axis=2), clips=clips, **{"hist%%d" %% s: eng.getHistory(s) for s in range(len(chain))})
 ''' % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -400,7 +400,7 @@ eng = jb.BatchProcessor([%r], %d)
 for slot, pid, v in %r:
     eng.setParameter(pid, v, slot)
 eng.set_path("lane"); eng.set_math_mode(%r)
-eng.prepareToPlay(48000.0, 512); eng.enableHistory(16)
+eng.prepareToPlay(48000.0, 512); eng.enableHistory(64)
 a = eng.processBlock(clips[:, :, :1024]); b = eng.processBlock(clips[:, :, 1024:])
 np.savez(sys.argv[1], out=np.concatenate([a, b], axis=2), hist=eng.getHistory(0), clips=clips)
 ''' % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -484,3 +484,19 @@ def test_mono_bus_matches_oracle(chain, jb, port):
         assert_samples_close(got, ref, "%s mono clip %d" % ("+".join(chain), c))
         for s in range(len(chain)):
             assert_records_close(recs[s][c], last[s], "%s mono clip %d slot %d" % ("+".join(chain), c, s))
+
+
+@pytest.mark.parametrize("chain", [FULL_CHAIN, ["JuicySaturator", "JuicyWidth", "JuicyCohere"]], ids=["full-chain", "light-chain"])
+def test_pipelined_chain_is_bit_identical(chain, jb, port):
+    """Plugins of a chain on separate streams, pipelined over segments of whole blocks (JB_CHAIN_PIPELINE=1), against one
+    launch per plugin over the whole call (=0): same samples, same per-block records, in place and with history."""
+    import tempfile
+    n_clips, n = 40, 23 * BLOCK + 100
+    with tempfile.TemporaryDirectory() as tmp:
+        res = {m: _render_in_fresh_process({"JB_CHAIN_PIPELINE": m}, chain, [], "auto", n_clips, n, tmp, "p" + m) for m in ("0", "1")}
+    assert np.array_equal(res["0"]["out"].view(np.uint32), res["1"]["out"].view(np.uint32)), \
+        "max diff %g" % float(np.abs(res["0"]["out"] - res["1"]["out"]).max())
+    for s in range(len(chain)):
+        assert np.array_equal(res["0"]["hist%d" % s].view(np.uint32), res["1"]["hist%d" % s].view(np.uint32)), s
+    ref, h = port.run_chain(chain, res["1"]["clips"][5], sample_rate=SAMPLE_RATE, block_size=BLOCK)
+    assert_samples_close(res["1"]["out"][5], ref, "clip 5")
