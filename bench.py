@@ -312,8 +312,14 @@ def run_engine_arm(args):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     all_cpus = bind_to_gpu_numa_node(local)
+    stdout_fd = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version (the image sets NCCL_DEBUG=VERSION) and any debug lines on fd 1; the contract is ONE JSON
+        # line on stdout, so everything goes to stderr until that line is written
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     jb = load_juicy_batch()
@@ -456,7 +462,11 @@ def run_engine_arm(args):
             del d_in, d_out, local_rec
             torch.cuda.empty_cache()
             line["other_configs"] = survey_other_configs(jb, local, peak)
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     try:
         eng.close()
     except Exception:
