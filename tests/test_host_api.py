@@ -93,3 +93,18 @@ def test_host_synth_shapes(jb):
     m = jb.synth_clips("mixed", 0, 4, 256)
     for k, kind in enumerate(("sweep", "noise", "impulse", "drum")):
         assert np.array_equal(m[k], jb.synth_clips(kind, k, 1, 256)[0])
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/juicy_batch.h must stay a C header (the reference-side binding may be C, cgo, ...): compile a C99 program
+    against it with -pedantic, link the library, run the host-only part (device -1: parameter logic without a GPU)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "juicy-audio-plugins_b200")
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c_abi_smoke.c"), "-o", exe, "-L", pkg, "-ljuicy_batch",
+                           "-Wl,-rpath," + pkg])
+    out = subprocess.check_output([exe]).decode()
+    assert out.startswith("sets 4 state bytes"), out
