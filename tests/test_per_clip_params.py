@@ -213,3 +213,37 @@ def test_parameter_sets_do_not_change_untouched_clips(jb):
     eng.close()
     assert np.array_equal(got[1::2], want[1::2])
     assert not np.array_equal(got[0::2], want[0::2])
+
+
+@pytest.mark.gpu
+def test_mono_bus_with_per_clip_parameters_and_automation(jb, port):
+    """The one-channel kernel under clip maps and a parameter schedule."""
+    n_clips, n = 21, 6 * BLOCK + 36
+    chain = ["JuicySaturator", "JuicyTexture", "JuicyMotion"]
+    clips = jb.synth_clips("mixed", 8, n_clips, n, 1)
+    eng = jb.BatchProcessor(chain, n_clips, n_channels=1)
+    eng.set_math_mode("fast")
+    for c in range(0, n_clips, 2):
+        eng.setParameterClips("material", 4.0, c, 1, 1)
+    eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+    eng.scheduleParameter("drive", 3, 11.0, 0)
+    out = eng.processBlock(clips)
+    rec = eng.getLatestMetrics(2)
+    eng.close()
+    for c in range(n_clips):
+        plugs = [port.PortPlugin(p, 1, SAMPLE_RATE, BLOCK) for p in chain]
+        if c % 2 == 0:
+            plugs[1].set_param("material", 4.0)
+        for p in plugs:
+            p.prepare()
+        outs, last = [], None
+        for t0, t1, drive in ((0, 3 * BLOCK, None), (3 * BLOCK, n, 11.0)):
+            if drive is not None:
+                plugs[0].set_param("drive", drive)
+            cur = clips[c][:, t0:t1]
+            for p in plugs:
+                cur, h = p.process(cur)
+            outs.append(cur)
+            last = h[-1]
+        assert_samples_close(out[c], np.concatenate(outs, axis=1), "mono clip %d" % c)
+        assert_records_close(rec[c], last, "mono clip %d" % c)
