@@ -1,3 +1,6 @@
+"""dbg_wood.py -- how far a chain drifts from the oracle when Punch / Saturator run their MUFU-based tanh / pow in front of
+each Texture material (the measurement behind csrc/jb_libm.h; output kept in profiles/r01_s6_chain_sensitivity.txt).
+Force the fast routines with eng.set_math_mode("fast") to reproduce it now that auto mode switches to the exact ones."""
 import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -34,4 +37,3 @@ run(["JuicyPunch", "JuicyTexture"], [(1, "material", 2.0)])
 run(["JuicySaturator", "JuicyTexture"], [(1, "material", 2.0)])
 run(["JuicyTexture"], [(0, "material", 2.0)])
 run(["JuicyTexture"], [(0, "material", 3.0)])
-os.environ["X"]="1"
