@@ -1017,6 +1017,11 @@ __device__ __forceinline__ void store4(float* p, int i, int n, bool vec, const Q
 #define JB_LF_AHEAD 6  // quads in flight per row (<= JB_LF_RING - 2: the octet loop issues two before it waits)
 #endif
 constexpr int LF_RING = JB_LF_RING, LF_AHEAD = JB_LF_AHEAD;
+// The four-samples-per-trip path (uncached row pieces) looks further ahead: in place (out == in -- every host-buffer render,
+// every plugin of a chain after the first) a load that lands in the 128-byte line the lane is currently storing to waits
+// for those stores in L2; 10 quads (160 bytes) ahead always reach past that line (profiles/r01_s6_inplace.txt: the
+// channel-per-lane kernel ran 2.2x slower in place with 6 ahead, the one-lane kernels 1.2x).  16-quad ring: 16 KB per warp.
+constexpr int LF4_RING = 16, LF4_AHEAD = 10;
 
 __device__ __forceinline__ uint32_t lf_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 // CACHE_L1: the 32-byte sector a piece belongs to is kept in L1, so the row's next piece does not go to L2 again
@@ -1050,21 +1055,23 @@ __device__ __forceinline__ float4* lane_smem()
 }
 inline size_t lane_smem_bytes(int octets)
 {
-    return octets == 2 ? (size_t) TILE_STAGES * TILE_STAGE_BYTES : (size_t) JB_LANE_CTA_THREADS * 2 * LF_RING * 16;
+    return octets == 2 ? (size_t) TILE_STAGES * TILE_STAGE_BYTES
+                       : (size_t) JB_LANE_CTA_THREADS * 2 * (octets == 1 ? LF_RING : LF4_RING) * 16;
 }
 __device__ __forceinline__ void lf_sts(uint32_t addr, const Quad& q)
 {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(q.v[0]), "f"(q.v[1]), "f"(q.v[2]), "f"(q.v[3]) : "memory");
 }
 
-struct LaneFeed {
+template <int RING>
+struct LaneFeedT {
     uint32_t base;           // shared address of this lane's 256-byte ring (row L, then row R), swizzle folded in
     const float *srcL, *srcR;
     int nQuads;
     __device__ __forceinline__ void init(const float* l, const float* r, int n)
     {
         float4* ring = lane_smem();
-        base = lf_smem_u32(&ring[threadIdx.x * 2 * LF_RING]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
+        base = lf_smem_u32(&ring[threadIdx.x * 2 * RING]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
         asm volatile("" : "+r"(base));
         srcL = l;
         srcR = r;
@@ -1074,17 +1081,17 @@ struct LaneFeed {
     __device__ __forceinline__ void issue(int q) const // quad q of both rows -> ring piece q & 7; always commits a group
     {
         if (q < nQuads) {
-            const uint32_t off = (uint32_t) (q & (LF_RING - 1)) << 4;
+            const uint32_t off = (uint32_t) (q & (RING - 1)) << 4;
             lf_cp_async16<CACHE_L1>(base ^ off, srcL + 4 * q);
-            lf_cp_async16<CACHE_L1>((base ^ off) + 16u * LF_RING, srcR + 4 * q);
+            lf_cp_async16<CACHE_L1>((base ^ off) + 16u * RING, srcR + 4 * q);
         }
         lf_commit();
     }
     __device__ __forceinline__ void read(int q, Quad& l, Quad& r) const
     {
-        const uint32_t off = (uint32_t) (q & (LF_RING - 1)) << 4;
+        const uint32_t off = (uint32_t) (q & (RING - 1)) << 4;
         l = lf_lds(base ^ off);
-        r = lf_lds((base ^ off) + 16u * LF_RING);
+        r = lf_lds((base ^ off) + 16u * RING);
     }
 };
 
@@ -1258,19 +1265,19 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
             quad(ql, qr, i, kWhole);
         }
     } else if (vec) { // every quad is whole (n % 4 == 0): rows come through the lane's prefetch ring
-        LaneFeed feed;
-        feed.init(srcL, srcR, n);
         if (Main::kHeavy || !a.octets) {
+            LaneFeedT<LF4_RING> feed;
+            feed.init(srcL, srcR, n);
 #pragma unroll
-            for (int q = 0; q < LF_AHEAD; ++q)
-                feed.issue<false>(q);
-            lf_wait<LF_AHEAD - 1>();
+            for (int q = 0; q < LF4_AHEAD; ++q)
+                feed.template issue<false>(q);
+            lf_wait<LF4_AHEAD - 1>();
             Quad ql, qr, nl, nr;
             feed.read(0, ql, qr);
 #pragma unroll 1
             for (int i = 0, q = 0; i < n; i += 4, ++q) {
-                feed.issue<false>(q + LF_AHEAD);
-                lf_wait<LF_AHEAD - 1>(); // quads <= q + 1 have landed
+                feed.template issue<false>(q + LF4_AHEAD);
+                lf_wait<LF4_AHEAD - 1>(); // quads <= q + 1 have landed
                 feed.read(q + 1, nl, nr);
                 quad(ql, qr, i, kWhole);
                 ql = nl;
@@ -1278,6 +1285,8 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
             }
             lf_wait<0>();
         } else {
+            LaneFeedT<LF_RING> feed;
+            feed.init(srcL, srcR, n);
 #pragma unroll
             for (int q = 0; q < LF_AHEAD; ++q)
                 feed.issue<true>(q);

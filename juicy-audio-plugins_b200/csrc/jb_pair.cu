@@ -17,7 +17,17 @@ namespace {
 
 using namespace jbdev;
 
-constexpr int PF_AHEAD = 6; // quads in flight (ring: 8 quads = 128 B per lane, 4 KB per warp)
+// Quads in flight per lane, and the ring that holds them.  In place (out == in: every host-buffer render, every plugin of a
+// chain after the first) a load that lands in the 128-byte line the lane is currently storing to waits for those stores in
+// L2 -- with 6 quads (96 bytes) ahead that was most loads, and the kernel ran 2.2x slower in place than out of place
+// (profiles/r01_s6_inplace.txt).  Ten quads ahead always reach past the line being written.
+#ifndef JB_PF_AHEAD
+#define JB_PF_AHEAD 10
+#endif
+#ifndef JB_PF_RING
+#define JB_PF_RING 16
+#endif
+constexpr int PF_AHEAD = JB_PF_AHEAD, PF_RING = JB_PF_RING; // ring: 16 quads = 256 B per lane, 8 KB per warp // quads in flight (ring: 8 quads = 128 B per lane, 4 KB per warp)
 
 struct LaneFeed1 {
     uint32_t base;
@@ -25,8 +35,9 @@ struct LaneFeed1 {
     int nQuads;
     __device__ __forceinline__ void init(const float* p, int n)
     {
-        __shared__ __align__(128) float4 ring[JB_LANE_CTA_THREADS * 8];
-        base = lf_smem_u32(&ring[threadIdx.x * 8]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
+        static_assert(PF_AHEAD + 2 <= PF_RING && (PF_RING & (PF_RING - 1)) == 0, "ring must hold the quads in flight");
+        __shared__ __align__(256) float4 ring[JB_LANE_CTA_THREADS * PF_RING];
+        base = lf_smem_u32(&ring[threadIdx.x * PF_RING]) ^ ((uint32_t) (threadIdx.x & 7) << 4);
         asm volatile("" : "+r"(base));
         src = p;
         nQuads = n >> 2;
@@ -34,10 +45,14 @@ struct LaneFeed1 {
     __device__ __forceinline__ void issue(int q) const
     {
         if (q < nQuads)
-            lf_cp_async16<false>(base ^ ((uint32_t) (q & 7) << 4), src + 4 * q);
+#ifdef JB_PAIR_CA
+            lf_cp_async16<true>(base ^ ((uint32_t) (q & (PF_RING - 1)) << 4), src + 4 * q);
+#else
+            lf_cp_async16<false>(base ^ ((uint32_t) (q & (PF_RING - 1)) << 4), src + 4 * q);
+#endif
         lf_commit();
     }
-    __device__ __forceinline__ Quad read(int q) const { return lf_lds(base ^ ((uint32_t) (q & 7) << 4)); }
+    __device__ __forceinline__ Quad read(int q) const { return lf_lds(base ^ ((uint32_t) (q & (PF_RING - 1)) << 4)); }
 };
 
 __device__ __forceinline__ float xchg(unsigned mask, float v) { return __shfl_xor_sync(mask, v, 1); }
@@ -357,7 +372,13 @@ __global__ void __launch_bounds__(JB_CTA_THREADS, MIN_CTAS) jb_pair_kernel(const
                 an.step(mask, ch, l, r, 0.5f * (l + r), y, ana);
                 cur.v[k] = y;
             }
+#if defined(JB_PAIR_STORE_CS)
+            asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(cur.v[0]), "f"(cur.v[1]), "f"(cur.v[2]), "f"(cur.v[3]) : "memory");
+#elif defined(JB_PAIR_STORE_CG)
+            asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(cur.v[0]), "f"(cur.v[1]), "f"(cur.v[2]), "f"(cur.v[3]) : "memory");
+#else
             *reinterpret_cast<float4*>(dst + i) = make_float4(cur.v[0], cur.v[1], cur.v[2], cur.v[3]);
+#endif
             cur = nxt;
         }
         lf_wait<0>();

@@ -29,11 +29,13 @@ __global__ void __launch_bounds__(JB_CTA_THREADS, MIN_CTAS) jb_single_kernel(con
 template <class Main, class Pre>
 cudaError_t launch_single(const ProcArgs& a, int grid, cudaStream_t stream)
 {
+    // heavy plugins always take the four-samples-per-trip path, whatever `octets` says: size the ring for it
+    const size_t smem = lane_smem_bytes(Main::kHeavy ? 0 : a.octets);
     // warps per SM this batch can supply; the 255-register variant holds at most 8
     if (Main::kHeavy && grid <= 8 * 148)
-        jb_single_kernel<Main, Pre, 8><<<grid, JB_CTA_THREADS, lane_smem_bytes(a.octets), stream>>>(a);
+        jb_single_kernel<Main, Pre, 8><<<grid, JB_CTA_THREADS, smem, stream>>>(a);
     else
-        jb_single_kernel<Main, Pre, 16><<<grid, JB_CTA_THREADS, lane_smem_bytes(a.octets), stream>>>(a);
+        jb_single_kernel<Main, Pre, 16><<<grid, JB_CTA_THREADS, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
