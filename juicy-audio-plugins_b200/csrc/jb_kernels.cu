@@ -92,10 +92,11 @@ long long g_launches = 0;
 // JB_LANE_GENERIC=1: single-plugin launches also take the generic kernel (A/B timing, tests of the generic path)
 const int g_pairMode = [] { const char* v = getenv("JB_PAIR"); return v == nullptr ? -1 : atoi(v); }();
 int envInt(const char* name, int dflt) { const char* v = getenv(name); return v == nullptr ? dflt : atoi(v); }
-// measured (profiles/r01_s6_pair.txt): Texture 8192 clips 1.5-1.7x faster in pairs, 16384 1.1x, 32768 0.9x; Saturator / Punch
-// with the MUFU math 1.4x at 8192, 0.9x at 16384; with the exact routines (long per-channel chains) faster at every size
-const int g_pairLimitTexture = envInt("JB_PAIR_LIMIT_TEXTURE", 16384), g_pairLimitExact = envInt("JB_PAIR_LIMIT_EXACT", 1 << 30),
-          g_pairLimitFast = envInt("JB_PAIR_LIMIT_FAST", 10240);
+// measured in place (profiles/r01_s6_pair.txt, last block): Texture 8192 clips 1.6x faster in pairs, 16384 / 24576 1.07-1.1x,
+// 32768 0.87x; Saturator / Punch with the MUFU math 1.45x at 8192, ~1.1x at 16384 / 24576 (0.93x around 12288), 0.7x at
+// 32768 where the one-lane kernel switches to eight samples per trip; with the exact routines faster at every size
+const int g_pairLimitTexture = envInt("JB_PAIR_LIMIT_TEXTURE", 24576), g_pairLimitExact = envInt("JB_PAIR_LIMIT_EXACT", 1 << 30),
+          g_pairLimitFast = envInt("JB_PAIR_LIMIT_FAST", 24576);
 const bool g_forceGeneric = [] { const char* v = getenv("JB_LANE_GENERIC"); return v != nullptr && atoi(v) != 0; }();
 
 int check(cudaError_t e, const char* what)
