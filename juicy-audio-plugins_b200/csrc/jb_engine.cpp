@@ -728,7 +728,10 @@ int renderClips(jb_engine* e, const float* dIn, float* dOut, int ns, int nc, lon
                 JB_CUDA(cudaStreamWaitEvent(st, e->groupFork, 0));
                 usedStream[next] = true;
             }
-            next = (next + 1) % kPool;
+            // three launches side by side: more DIFFERENT kernels on the SMs at once cost more than they overlap (C3, five
+            // Texture materials on 8192 clips: 1 stream 58 ms, 2 30.5, 3 27.1, 5 37.3 -- profiles/r01_s6_survey_single.txt)
+            static const int poolUse = [] { const char* v = std::getenv("JB_GROUP_STREAMS"); return v == nullptr ? 3 : std::min((int) jb_engine::kGroupStreams, std::max(1, std::atoi(v))); }();
+            next = (next + 1) % poolUse;
         }
         if (int rc = launchKernels(e, a, st, serial))
             return rc;
