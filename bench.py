@@ -267,6 +267,8 @@ def survey_other_configs(jb, device, peak_gbs):
     for name, chain, n_clips, n, synth, clipmod in specs:
         try:
             buf = jb.DeviceBuffer(n_clips * 2 * n * 4, device)
+            # the big configurations render in place (C4 is 25 GB of input); C3's five concurrent launches go out of place
+            dst = jb.DeviceBuffer(n_clips * 2 * n * 4, device) if clipmod else buf
             jb.synth_fill_device(buf.ptr.value, synth, 0, n_clips, 2, n, SAMPLE_RATE, device=device, stream=0)
             eng = jb.BatchProcessor(chain, n_clips, device=device)
             if clipmod:
@@ -275,13 +277,13 @@ def survey_other_configs(jb, device, peak_gbs):
                     eng.setParameterClips(pid, float(c % k), c, 1, 0)
             eng.prepareToPlay(SAMPLE_RATE, BLOCK)
             eng.reset()
-            eng.process_device(buf.ptr.value, buf.ptr.value, n)
+            eng.process_device(buf.ptr.value, dst.ptr.value, n)
             eng.synchronize()
             eng.kernel_time_ms()
             steps = 2
             for _ in range(steps):
                 eng.reset()
-                eng.process_device(buf.ptr.value, buf.ptr.value, n)
+                eng.process_device(buf.ptr.value, dst.ptr.value, n)
             ms, launches = eng.kernel_time_ms()
             ms /= steps
             ch_samples = n_clips * 2 * n
@@ -290,9 +292,11 @@ def survey_other_configs(jb, device, peak_gbs):
             alg = (4.0 if read_only else 8.0) * ch_samples + 64.0 * n_clips * n_blocks * len(chain)
             out.append({"workload": name, "chain": chain, "clips": n_clips, "samples_per_clip": n, "ms_per_render": ms,
                         "launches_per_render": launches / steps, "value": ch_samples / (ms / 1000.0), "unit": UNIT,
-                        "algorithmic_bytes": alg, "frac_of_hbm_peak": alg / (ms / 1000.0) / 1e9 / peak_gbs,
+                        "in_place": dst is buf, "algorithmic_bytes": alg, "frac_of_hbm_peak": alg / (ms / 1000.0) / 1e9 / peak_gbs,
                         "math": "auto (fast: no resonant Texture material behind a shaper in these configurations)"})
             eng.close()
+            if dst is not buf:
+                dst.free()
             buf.free()
         except Exception as exc:  # a survey line must never take the bench line down
             out.append({"workload": name, "error": str(exc)})
