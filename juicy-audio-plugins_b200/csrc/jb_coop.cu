@@ -602,7 +602,7 @@ struct CoopArgs {
     float* monoScratch; // [grid][CO_GMAX][chainLen + 1][2][CO_BLOCKMAX]
     int groupClips;     // clips per group (<= CO_GMAX)
     int numGroups;
-    int debugSkip;      // profiling aid (JB_COOP_DEBUG_SKIP): bit 0 envelope walk, 1 band walk, 2 bulk math, 3 scout
+    int debugSkip;      // profiling builds (-DJB_COOP_DEBUG, JB_COOP_DEBUG_SKIP): bit 0 envelope walk, 1 band walk, 2 bulk math, 3 scout
 };
 
 __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_constant__ CoopArgs ca)
@@ -614,6 +614,11 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
     const int L = a.chainLen;
     const int nSig = L + 1;
     const AnaCoef& ana = a.ana; // stays in the kernel-parameter constant bank
+#ifdef JB_COOP_DEBUG
+    const int dbgSkip = ca.debugSkip; // profiling builds only (-DJB_COOP_DEBUG): skip roles to see what the others cost
+#else
+    constexpr int dbgSkip = 0;        // release builds: no environment variable can change what is rendered
+#endif
 
     // roles (uniform over the launch)
     const int nAna = (L * ca.groupClips + 31) / 32;          // envelope-analyzer warps; as many band-analyzer warps
@@ -721,7 +726,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
         auto scout_step = [&](const Cursor& c, unsigned step) {
             const int slot = step & 1;
             mbar_wait(&sm.bar[slot], (step >> 1) & 1);
-            if (!isScout || (ca.debugSkip & 8))
+            if (!isScout || (dbgSkip & 8))
                 return;
             const PunchCoef& pc = a.slot[0].c.punch;
             const float4* src = reinterpret_cast<const float4*>(&sm.tile[slot][scRow][0]);
@@ -749,13 +754,13 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             ++anaCalls;
             AnaAcc acc;
             const float* stream = monoCta + ((size_t) anaClip * nSig + sig) * 2 * CO_BLOCKMAX + par * CO_BLOCKMAX;
-            if (ca.debugSkip & 16) // probe: every walk re-reads one L1-resident kilobyte per lane
+            if (dbgSkip & 16) // probe: every walk re-reads one L1-resident kilobyte per lane
                 stream = monoCta + (size_t) anaIdx * 256;
             AnaFeed feed;
             feed.stream = stream;
             feed.laneBase = anaLaneBase;
             feed.policy = polKeep;
-            if (isAna && !(ca.debugSkip & (isBandWarp ? 2 : 1))) {
+            if (isAna && !(dbgSkip & (isBandWarp ? 2 : 1))) {
                 if (isBandWarp) {
                     ana_walk<true>(ast, acc, feed, n, ana);
                     sm.bandAcc[hand][anaIdx][0] = acc.lowAcc;
@@ -766,7 +771,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             }
             named_barrier(CO_BAR_ANA, anaThreads);
             Metrics m {};
-            if (isAna && isEnvWarp && !(ca.debugSkip & 32)) {
+            if (isAna && isEnvWarp && !(dbgSkip & 32)) {
                 acc.lowAcc = sm.bandAcc[hand][anaIdx][0];
                 acc.highAcc = sm.bandAcc[hand][anaIdx][1];
                 m = ana_finish(ast, acc, load_stats(sm.stats[par][anaClip][sig]), n, ana);
@@ -824,7 +829,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                 const int nValid = max(0, min(CO_CH, cur.n - lane * CO_CH));
                 const bool firstStep = cur.off == 0;
                 const bool ragged = cur.n < CO_T; // warp-uniform
-                for (int ci = parIdx - wBulk; ci < G && !(ca.debugSkip & 4); ci += nBulk) {
+                for (int ci = parIdx - wBulk; ci < G && !(dbgSkip & 4); ci += nBulk) {
                     float* rowL = &sm.tile[slot][2 * ci][lane * CO_CH];
                     float* rowR = &sm.tile[slot][2 * ci + 1][lane * CO_CH];
                     float l[CO_CH], r[CO_CH];
@@ -984,8 +989,12 @@ int jbk_launch_coop(const ProcArgs* args, float* monoScratch, int numSMs, void* 
         g = CO_GMAX;
     ca.groupClips = g;
     ca.numGroups = (args->nClips + g - 1) / g;
+#ifdef JB_COOP_DEBUG
     const char* dbg = getenv("JB_COOP_DEBUG_SKIP");
     ca.debugSkip = dbg ? atoi(dbg) : 0;
+#else
+    ca.debugSkip = 0;
+#endif
     const int grid = ca.numGroups < numSMs ? ca.numGroups : numSMs;
     jb_coop_kernel<<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
     jbk_note_launch();

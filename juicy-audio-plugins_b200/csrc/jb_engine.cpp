@@ -110,7 +110,7 @@ struct jb_engine {
     float* dStage[3] = { nullptr, nullptr, nullptr };
     std::vector<cudaEvent_t> sliceEvents;
     cudaEvent_t evIn[3] = {}, evDone[3] = {}, evOut[3] = {};
-    size_t stageBytes = 0;
+    size_t stageBytes[3] = { 0, 0, 0 }; // capacity of each staging buffer (they grow independently)
 
     std::vector<float> hostScratch;
 
@@ -201,7 +201,7 @@ void freeDevice(jb_engine* e)
         if (e->evOut[i]) cudaEventDestroy(e->evOut[i]);
         e->evIn[i] = e->evDone[i] = e->evOut[i] = nullptr;
     }
-    e->stageBytes = 0;
+    e->stageBytes[0] = e->stageBytes[1] = e->stageBytes[2] = 0;
     if (e->copyIn) cudaStreamDestroy(e->copyIn);
     if (e->copyOut) cudaStreamDestroy(e->copyOut);
     e->copyIn = e->copyOut = nullptr;
@@ -268,6 +268,7 @@ int fillVar(jb_engine* e, int var, float value)
 int resetState(jb_engine* e)
 {
     const auto inits = stateInits(e);
+    const bool constructed = e->stateConstructed;
     if (!e->stateConstructed) {
         JB_CUDA(cudaMemsetAsync(e->dState, 0, sizeof(float) * (size_t) e->totalVars * (size_t) e->clipPitch, e->stream));
         for (const auto& i : inits)
@@ -290,12 +291,14 @@ int resetState(jb_engine* e)
         JB_CUDA(cudaMemsetAsync(e->dRing, 0, sizeof(float) * (size_t) e->ringLen * (size_t) e->clipPitch, e->stream));
     if (e->dWave)
         JB_CUDA(cudaMemsetAsync(e->dWave, 0, sizeof(float) * 2 * (size_t) e->waveLen * (size_t) e->clipPitch, e->stream));
-    JB_CUDA(cudaMemsetAsync(e->dLatest, 0, sizeof(float) * e->chain.size() * JBK_REC * (size_t) e->clipPitch, e->stream));
-    {   // getLatestMetrics() before any block: monoSafety mailbox starts at 1 (e.g. JuicyPunch/PluginProcessor.h:51)
+    if (!constructed) {
+        // The latest* mailboxes are constructor-initialised members (monoSafety = 1, the rest 0: e.g.
+        // JuicyPunch/PluginProcessor.h:44-51); prepareToPlay never touches them, so getLatestMetrics() after a re-prepare
+        // still returns the previous block's values.
+        JB_CUDA(cudaMemsetAsync(e->dLatest, 0, sizeof(float) * e->chain.size() * JBK_REC * (size_t) e->clipPitch, e->stream));
         for (size_t s = 0; s < e->chain.size(); ++s)
-            if (e->chain[s] != jb::kInfer || true)
-                if (jbk_launch_fill(e->dLatest + ((long long) s * JBK_REC + 12) * e->clipPitch, 1.0f, e->clipPitch, e->stream) != 0)
-                    return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
+            if (jbk_launch_fill(e->dLatest + ((long long) s * JBK_REC + 12) * e->clipPitch, 1.0f, e->clipPitch, e->stream) != 0)
+                return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
     }
     if (e->dHist)
         JB_CUDA(cudaMemsetAsync(e->dHist, 0, sizeof(float) * (size_t) e->histMaxBlocks * e->chain.size() * JBK_REC * (size_t) e->clipPitch, e->stream));
@@ -377,10 +380,8 @@ int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params
     }
     if (e->chain.size() == 1)
         a.octets = octetsFor(e->chain[0], nClips, nSamples, false, a.exactMath != 0);
-    if (e->nCh == 1) { // mono buses run the generic kernel's one-channel instantiation: fast math, four samples per trip
-        a.exactMath = 0;
+    if (e->nCh == 1) // mono buses run the generic kernel's one-channel instantiations (either math mode), four samples per trip
         a.octets = 0;
-    }
     a.ana = jb::makeAnaCoef(e->sampleRate);
     for (size_t s = 0; s < e->chain.size(); ++s) {
         a.slot[s].kind = e->chain[s];
@@ -406,20 +407,32 @@ int drainTiming(jb_engine* e)
     return JB_OK;
 }
 
-// Timing-event pair for one render on the engine's stream (jb_kernel_time_ms).
+// Timing-event pair for one render on the engine's stream (jb_kernel_time_ms).  Never blocks: when the pool is in use,
+// pairs whose stop event has already completed are folded into the running total (cudaEventQuery) and their events
+// recycled; if the device is further behind than that, the pool grows instead of waiting for it (jb_process stays
+// asynchronous and jb_process_host's upload / render / download overlap is not stalled).
 int timingPair(jb_engine* e, cudaEvent_t* start, cudaEvent_t* stop)
 {
-    if (e->timingUsed + 2 > e->timingEvents.size()) {
-        if (e->timingEvents.size() >= 256) {
-            if (int rc = drainTiming(e))
-                return rc;
-        } else {
-            for (int i = 0; i < 2; ++i) {
-                cudaEvent_t ev = nullptr;
-                JB_CUDA(cudaEventCreate(&ev));
-                e->timingEvents.push_back(ev);
+    if (e->timingUsed + 2 > e->timingEvents.size() && e->timingUsed >= 64) {
+        size_t done = 0;
+        while (done + 1 < e->timingUsed && cudaEventQuery(e->timingEvents[done + 1]) == cudaSuccess) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, e->timingEvents[done], e->timingEvents[done + 1]) == cudaSuccess) {
+                e->kernelMs += (double) ms;
+                ++e->kernelLaunches;
             }
+            done += 2;
         }
+        cudaGetLastError(); // cudaErrorNotReady from the query is not an error of ours
+        if (done > 0) { // recycle: completed pairs go to the back of the pool
+            std::rotate(e->timingEvents.begin(), e->timingEvents.begin() + (long) done, e->timingEvents.begin() + (long) e->timingUsed);
+            e->timingUsed -= done;
+        }
+    }
+    while (e->timingUsed + 2 > e->timingEvents.size()) {
+        cudaEvent_t ev = nullptr;
+        JB_CUDA(cudaEventCreate(&ev));
+        e->timingEvents.push_back(ev);
     }
     *start = e->timingEvents[e->timingUsed];
     *stop = e->timingEvents[e->timingUsed + 1];
@@ -1322,13 +1335,14 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
     const size_t need = clipBytes * (size_t) passClips;
     const int nBuffers = nPasses > 1 ? 2 : 1;
     for (int i = 0; i < nBuffers; ++i) {
-        if (e->dStage[i] == nullptr || need > e->stageBytes) {
+        if (e->dStage[i] == nullptr || need > e->stageBytes[i]) {
             cudaFree(e->dStage[i]);
             e->dStage[i] = nullptr;
+            e->stageBytes[i] = 0;
             JB_CUDA(cudaMalloc(&e->dStage[i], need));
+            e->stageBytes[i] = need;
         }
     }
-    e->stageBytes = std::max(e->stageBytes, need);
     while (e->sliceEvents.size() < (size_t) 2 * (size_t) nSlices) {
         cudaEvent_t ev = nullptr;
         JB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1336,6 +1350,13 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
     }
 
     const long long blocksBase = e->blocksDone;
+    // renderAutomated moves e->blocksDone while it walks the slices; whatever exit path is taken (a CUDA error return
+    // included) the counter ends at the value the call began with, or past the whole render on success
+    struct BlocksGuard {
+        jb_engine* e;
+        long long value;
+        ~BlocksGuard() { e->blocksDone = value; }
+    } blocksGuard { e, blocksBase };
     int rcLaunch = JB_OK;
     // every pass walks the same stretch of time, so each starts from the parameters and schedule the call began with
     const bool replay = nPasses > 1 && !e->schedule.empty();
@@ -1381,10 +1402,9 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
     JB_CUDA(cudaStreamSynchronize(e->copyIn));
     JB_CUDA(cudaStreamSynchronize(e->stream));
     JB_CUDA(cudaStreamSynchronize(e->copyOut));
-    e->blocksDone = blocksBase;
     if (rcLaunch != JB_OK)
         return rcLaunch;
-    e->blocksDone += totalBlocks;
+    blocksGuard.value = blocksBase + totalBlocks;
     return JB_OK;
 }
 

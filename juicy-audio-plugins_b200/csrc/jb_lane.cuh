@@ -1367,7 +1367,9 @@ __device__ __forceinline__ void sweep_pre_dispatch(const ProcArgs& a, long long 
     }
 }
 
-template <bool MONO>
+// EXACT: Saturator / Punch with the C library's own tanh / pow (jb_libm.h); only the mono kernel instantiates it for a
+// whole chain (the stereo engines render exact-math chains plugin by plugin with the jb_single kernels).
+template <bool MONO, bool EXACT = false>
 __device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
 {
     if (mainSlot < 0) {
@@ -1377,8 +1379,8 @@ __device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, 
     const SlotDesc& d = a.slot[mainSlot];
     switch (d.kind) {
         case K_INFER: sweep_pre_dispatch<MainInfer, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_PUNCH: sweep_pre_dispatch<MainPunch<false>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
-        case K_SAT: sweep_pre_dispatch<MainSat<false>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_PUNCH: sweep_pre_dispatch<MainPunch<EXACT>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
+        case K_SAT: sweep_pre_dispatch<MainSat<EXACT>, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
         case K_WIDTH: sweep_pre_dispatch<MainWidth, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
         case K_COHERE: sweep_pre_dispatch<MainCohere, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
         case K_MOTION: sweep_pre_dispatch<MainMotion, MONO>(a, clip, mainSlot, pos, n, blockAbs); break;
@@ -1396,7 +1398,7 @@ __device__ void sweep_dispatch(const ProcArgs& a, long long clip, int mainSlot, 
 }
 
 
-template <bool MONO>
+template <bool MONO, bool EXACT = false>
 __global__ void __launch_bounds__(JB_CTA_THREADS, 16) jb_process_kernel(const __grid_constant__ ProcArgs a)
 {
     const long long lane = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -1407,7 +1409,7 @@ __global__ void __launch_bounds__(JB_CTA_THREADS, 16) jb_process_kernel(const __
     for (int pos = 0; pos < a.nSamples; pos += a.blockSize, ++blockAbs) {
         const int n = min(a.blockSize, a.nSamples - pos);
         for (int s = -1; s < a.chainLen; ++s)
-            sweep_dispatch<MONO>(a, clip, s, pos, n, blockAbs);
+            sweep_dispatch<MONO, EXACT>(a, clip, s, pos, n, blockAbs);
     }
 }
 

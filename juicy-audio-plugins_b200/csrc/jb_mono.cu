@@ -4,6 +4,11 @@
 
 extern "C" int jbk_launch_mono(const ProcArgs* args, int grid, void* stream)
 {
-    jb_process_kernel<true><<<grid, JB_CTA_THREADS, lane_smem_bytes(0), (cudaStream_t) stream>>>(*args);
+    // exact math (JB_MATH_EXACT, or JB_MATH_AUTO with a shaper in front of another plugin): the instantiation whose
+    // Saturator / Punch call the C library's own tanh / pow, so a mono chain honours the math mode like a stereo one
+    if (args->exactMath)
+        jb_process_kernel<true, true><<<grid, JB_CTA_THREADS, lane_smem_bytes(0), (cudaStream_t) stream>>>(*args);
+    else
+        jb_process_kernel<true, false><<<grid, JB_CTA_THREADS, lane_smem_bytes(0), (cudaStream_t) stream>>>(*args);
     return (int) cudaGetLastError();
 }

@@ -40,7 +40,7 @@ const std::vector<ParamSpec> kSpecs[kNumKinds] = {
       F("mix", "Mix", 0.0f, 1.0f, 1.0f), F("output", "Output (dB)", -18.0f, 18.0f, -3.0f),
       F("juiciness", "Juiciness Score", 0.0f, 100.0f, 0.0f, true) },
     // JuicyWidth/PluginProcessor.cpp:229-239
-    { F("width", "Width", 0.0f, 1.0f, 0.45f), F("haasMs", "Haas (ms)", 0.0f, 35.0f, 12.0f), F("monoSafe", "Mono Safe", 0.0f, 1.0f, 0.7f),
+    { F("width", "Stereo Width", 0.0f, 1.0f, 0.45f), F("haasMs", "Haas Delay (ms)", 0.0f, 35.0f, 12.0f), F("monoSafe", "Mono Safety", 0.0f, 1.0f, 0.7f),
       F("mix", "Mix", 0.0f, 1.0f, 1.0f), F("output", "Output (dB)", -18.0f, 18.0f, 0.0f),
       F("juiciness", "Juiciness Score", 0.0f, 100.0f, 0.0f, true) },
     // JuicyCohere/PluginProcessor.cpp:166-178

@@ -69,6 +69,12 @@ const char* ref_param_id(void* p, int i)
     return static_cast<Host*>(p)->apvts->getParameterByIndex(i)->paramID.toStdString().c_str();
 }
 
+// display name as createParameterLayout() gives it (what a host shows next to the control)
+const char* ref_param_name(void* p, int i)
+{
+    return static_cast<Host*>(p)->apvts->getParameterByIndex(i)->name.toStdString().c_str();
+}
+
 void ref_param_range(void* p, int i, float* out3)
 {
     const auto& r = static_cast<Host*>(p)->apvts->getParameterByIndex(i)->getNormalisableRange();
