@@ -1,23 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- channel-samples/s of the JuicySuite hot path on B200 (BASELINE.json metric).
 
-Workload at every N: configs[1] of BASELINE.json per GPU -- the JuicyPunch -> JuicyWidth chain on
-4096 stereo drum-hit clips (1 s, 48 kHz, 512-sample blocks), weak scaling (each rank renders its
-own 4096 clips; clips are independent, so the data path has no collective; rank 0 gathers the
-per-clip Juiciness records with one NCCL all_gather, inside the timed region).
+Workloads (BASELINE.json `configs`, shapes of SURVEY.md §8(d)); `--config` picks one, the default is
+  N = 1 : C2 = configs[1], JuicyPunch -> JuicyWidth on 4096 stereo drum-hit clips (1 s, 48 kHz, 512-sample blocks) --
+          the configuration the metric is quoted on; C1 / C3 / C4 and one GPU's C5 shard follow in `other_configs`,
+          each with its own device-resident time, e2e, cpu_baseline and clocks;
+  N > 1 : C5 = configs[4], the full 7-plugin chain, 32768 stereo clips per GPU (262144 at 8 GPUs), weak scaling.
+Clips are independent plugin-instance chains, so rank r renders its own clips and the data path has no collective;
+the per-clip Juiciness records are gathered with ONE ncclAllGather per step issued by the library itself
+(jb_gather_records, NCCL resolved with dlopen), inside the timed region.
 
-A step = prepareToPlay-reset + one render of the whole batch, out of place (input buffer is
-1.57 GB, far larger than the 126 MB L2, so no step sees a warm cache).
-  value    : device-resident throughput (inputs already in HBM), CUDA events, max over ranks
-  e2e      : the same render through jb_process_host with pinned HOST buffers, H2D/D2H inside
-  roofline : algorithmic bytes per launch / mean device duration of the render kernel (events
-             recorded by the library around every launch on its stream) vs MEASURED_PEAKS.json
-  cpu_baseline / --impl reference : the reference's own C++ processBlock (oracle/_ref, or the C port
-             when the reference build is absent) on the box's host cores, bounded sample.
-torch is plumbing only (device buffers, streams/events, torch.distributed); the engine is
+A step = prepareToPlay-reset + one render of the whole batch, out of place (every input is far larger than the
+126 MB L2, so no step sees a warm cache).
+  value    : device-resident throughput (inputs already in HBM), CUDA events on the engine's stream, max over ranks
+  e2e      : the same render through jb_process_host with pinned HOST buffers, H2D + D2H inside the timed region
+  roofline : algorithmic bytes per render / mean device duration of the render (CUDA events recorded by the library
+             around its launches on its own stream) vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the reference's own C++ processBlock (oracle/_ref; the C port when that build is
+             absent) on the box's host cores, a bounded sample of the same workload.
+The default math mode (JB_MATH_AUTO) is measured: a Punch / Saturator that feeds another plugin runs the C library's own
+tanh / pow so that the chain's output is the reference's bit for bit; `fast_math` reports the same
+render with the special-function-unit routines (inside 1e-5 of peak for > 99.9 % of clips, not for all).
+torch is plumbing only (streams / events, torch.distributed for the barrier and the max over ranks); the engine is
 juicy-audio-plugins_b200/libjuicy_batch.so called through its C ABI.
 """
 import argparse
+import ctypes
 import importlib.util
 import json
 import os
@@ -32,24 +40,32 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "juicy-audio-plugins_b200")
 sys.path.insert(0, ROOT)
 
-CHAIN = ["JuicyPunch", "JuicyWidth"]
 SAMPLE_RATE = 48000.0
 BLOCK = 512
 METRIC = "channel-samples/sec per plugin chain"
 UNIT = "channel-samples/s"
+FULL_CHAIN = ["JuicyPunch", "JuicySaturator", "JuicyTexture", "JuicyWidth", "JuicyMotion", "JuicyCohere", "JuicyInfer"]
+
+# name -> workload (BASELINE.json configs[i]); per_clip = (slot, parameter id, modulus): value = clip index mod modulus
+WORKLOADS = {
+    "C1": {"label": "configs[0]: JuicySaturator processBlock on a 10 s 48 kHz stereo sine sweep, 512-sample blocks",
+           "chain": ["JuicySaturator"], "clips": 1, "samples": 480000, "synth": "sweep", "per_clip": None},
+    "C2": {"label": "configs[1]: JuicyPunch -> JuicyWidth chain on 4096 stereo drum-hit clips (1 s, 48 kHz) per GPU",
+           "chain": ["JuicyPunch", "JuicyWidth"], "clips": 4096, "samples": 48000, "synth": "drum", "per_clip": None},
+    "C3": {"label": "configs[2]: JuicyTexture resonator bank on 16384 impulse-train streams (8192 stereo instances), material = clip mod 5",
+           "chain": ["JuicyTexture"], "clips": 8192, "samples": 48000, "synth": "impulse", "per_clip": (0, "material", 5)},
+    "C4": {"label": "configs[3]: JuicyInfer pre/post scoring on 65536 noise / sweep / impulse / drum clips",
+           "chain": ["JuicyInfer"], "clips": 65536, "samples": 48000, "synth": "mixed", "per_clip": None},
+    "C5": {"label": "configs[4]: full 7-plugin chain (Punch->Saturator->Texture->Width->Motion->Cohere->Infer), 32768 stereo clips "
+                    "per GPU (one shard of 262144 clips over 8 GPUs)",
+           "chain": FULL_CHAIN, "clips": 32768, "samples": 48000, "synth": "mixed", "per_clip": None},
+}
 
 
 def load_juicy_batch():
     spec = importlib.util.spec_from_file_location("juicy_batch", os.path.join(PKG, "juicy_batch.py"))
     mod = importlib.util.module_from_spec(spec)
     sys.modules["juicy_batch"] = mod
-    spec.loader.exec_module(mod)
-    return mod
-
-
-def load_sharding():
-    spec = importlib.util.spec_from_file_location("jb_sharding", os.path.join(PKG, "sharding.py"))
-    mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
 
@@ -145,24 +161,59 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(w, name):
+    """The `config` object of the JSON line: identical for the engine arm and the reference arm."""
+    return {"workload": w["label"], "name": name, "chain": w["chain"], "clips_per_gpu": w["clips"], "channels": 2,
+            "samples_per_clip": w["samples"], "sample_rate": SAMPLE_RATE, "block_size": BLOCK,
+            "parameters": "plugin defaults (program 0)" + ("; %s = clip mod %d" % (w["per_clip"][1], w["per_clip"][2]) if w["per_clip"] else ""),
+            "input": w["synth"],
+            "cache": "inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed"
+                     % (w["clips"] * 2 * w["samples"] * 4 / 1e9) if w["clips"] * w["samples"] * 8 > 4e8 else
+                     "a 1.2 GB buffer is overwritten between timed renders (L2 flush): the clip itself fits the L2",
+            "sharding": "independent clips per rank, no data-path collective; one ncclAllGather of per-clip records per step"}
+
+
+def algorithmic_bytes(w):
+    """8 B per channel-sample per chain (4 read + 4 written; Infer with trim = 0 dB is read-only: 4)
+    plus one 64 B record per (clip, block, plugin)."""
+    ch_samples = w["clips"] * 2 * w["samples"]
+    n_blocks = (w["samples"] + BLOCK - 1) // BLOCK
+    per = 4.0 if w["chain"] == ["JuicyInfer"] else 8.0
+    return per * ch_samples + 64.0 * w["clips"] * n_blocks * len(w["chain"])
+
+
 # ---------------------------------------------------------------------------------------------- CPU reference
 
 def cpu_worker(spec):
-    """One host process of the CPU arm: its slice of the clips through the reference chain.
+    """One host process of the CPU arm: its slice of the clips through the reference chain.  Inputs come from the numpy
+    generator (oracle/synth_np.py): this process never loads the product library.
     (Threads of one process share a core in some sandboxes, so the CPU arm uses processes.)"""
-    jb = load_juicy_batch()
-    from oracle import refhost, port
+    from oracle import refhost, port, synth_np
     cls = refhost.RefPlugin if spec["kind"] == "reference" else port.PortPlugin
     lo, hi, n = spec["lo"], spec["hi"], spec["samples"]
-    clips = jb.synth_clips("drum", lo, hi - lo, n, 2, SAMPLE_RATE)
+    chain, per_clip = spec["chain"], spec.get("per_clip")
+    clips = synth_np.synth_clips(spec["synth"], lo, hi - lo, n, 2, SAMPLE_RATE)
     work = np.empty_like(clips)
     rec = np.zeros((hi - lo, 16), dtype=np.float32)
-    plugins = [cls(p, 2, SAMPLE_RATE, BLOCK) for p in CHAIN]
+    # one instance per (plugin, parameter value): per-clip values render as groups of clips, like the engine's parameter sets
+    variants = range(per_clip[2]) if per_clip else [None]
+    plugins = {}
+    for v in variants:
+        ps = [cls(p, 2, SAMPLE_RATE, BLOCK) for p in chain]
+        if v is not None:
+            ps[per_clip[0]].set_param(per_clip[1], float(v))
+        plugins[v] = ps
+    groups = {v: [c for c in range(lo, hi) if (c % per_clip[2]) == v] for v in variants} if per_clip else {None: list(range(lo, hi))}
 
     def render():
         np.copyto(work, clips)
-        for p in plugins:  # plugin by plugin == block by block: every plugin is causal with identical blocking
-            p.lib.render_clips(p.h, work.ctypes.data, hi - lo, n, BLOCK, SAMPLE_RATE, rec.ctypes.data)
+        for v, members in groups.items():
+            for p in plugins[v]:  # plugin by plugin == block by block: every plugin is causal with identical blocking
+                if per_clip:
+                    for c in members:
+                        p.lib.render_clips(p.h, work[c - lo].ctypes.data, 1, n, BLOCK, SAMPLE_RATE, rec[c - lo].ctypes.data)
+                else:
+                    p.lib.render_clips(p.h, work.ctypes.data, hi - lo, n, BLOCK, SAMPLE_RATE, rec.ctypes.data)
 
     for _ in range(spec["warmup"]):
         render()
@@ -178,56 +229,84 @@ def cpu_worker(spec):
     return 0
 
 
-def cpu_reference_run(n_clips, n_samples, procs, warmup, steps):
-    """The reference's own processBlock (oracle/_ref; the C port if that build is absent) over n_clips
-    drum-hit clips, split over `procs` host processes.  Returns (kind, processes used, seconds for `steps` passes)."""
+def cpu_reference_run(w, n_clips, procs, warmup, steps):
+    """The reference's own processBlock (oracle/_ref; the C port if that build is absent) over n_clips clips of workload
+    `w`, split over `procs` host processes.  Returns (kind, processes used, seconds for `steps` passes)."""
     from oracle import refhost, port
     if refhost.available():
         kind = "reference"
     else:
         kind = "port"
         port.lib()
+    procs = max(1, min(procs, n_clips))
     per = (n_clips + procs - 1) // procs
     slices = [(t * per, min(n_clips, (t + 1) * per)) for t in range(procs) if t * per < n_clips]
     env = dict(os.environ)
     env["CUDA_VISIBLE_DEVICES"] = ""
     workers = []
     for lo, hi in slices:
-        spec = {"kind": kind, "lo": lo, "hi": hi, "samples": n_samples, "warmup": warmup, "steps": steps}
+        spec = {"kind": kind, "lo": lo, "hi": hi, "samples": w["samples"], "warmup": warmup, "steps": steps,
+                "chain": w["chain"], "synth": w["synth"], "per_clip": w["per_clip"]}
         workers.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", json.dumps(spec)],
                                         stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=env))
-    for w in workers:
-        line = w.stdout.readline()
+    for wk in workers:
+        line = wk.stdout.readline()
         if line.strip() != "ready":
             raise RuntimeError("cpu worker failed to start: %r" % line)
-    for w in workers:
-        w.stdin.write("go\n")
-        w.stdin.flush()
-    stamps = [json.loads(w.stdout.readline()) for w in workers]
-    for w in workers:
-        w.wait()
+    for wk in workers:
+        wk.stdin.write("go\n")
+        wk.stdin.flush()
+    stamps = [json.loads(wk.stdout.readline()) for wk in workers]
+    for wk in workers:
+        wk.wait()
     seconds = max(s["end"] for s in stamps) - min(s["start"] for s in stamps)
     return kind, len(slices), seconds
 
 
+def cpu_sample_clips(w, threads, override=0):
+    """Bounded sample of the workload for the CPU legs: ~4 M channel-samples per host thread and pass, at least one clip
+    per thread where the workload has that many (C1 is a single clip: one process renders it)."""
+    if override:
+        return min(override, w["clips"])
+    per_thread = max(1, int(4.0e6 // (2 * w["samples"] * max(1, len(w["chain"]) // 2))))
+    return max(1, min(w["clips"], threads * per_thread))
+
+
+def cpu_baseline(w, threads, override=0, passes=2):
+    n_clips = cpu_sample_clips(w, threads, override)
+    kind, used, secs = cpu_reference_run(w, n_clips, threads, 1, passes)
+    return {"value": passes * n_clips * 2 * w["samples"] / secs, "unit": UNIT, "cores": used, "kind": kind,
+            "sample": "%d of the %d clips (x 2 ch x %d samples) through %s in %d-sample blocks, %d passes, %d host processes"
+                      % (n_clips, w["clips"], w["samples"], " -> ".join(w["chain"]), BLOCK, passes, used)}
+
+
+def pick_workload(args, world):
+    name = args.config or ("C2" if world <= 1 else "C5")
+    w = dict(WORKLOADS[name])
+    if args.clips:
+        w["clips"] = args.clips
+    if args.samples:
+        w["samples"] = args.samples
+    return name, w
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if rank != 0:
         return 0
-    jb = load_juicy_batch()
+    name, w = pick_workload(args, max(world, args.gpus))
     threads = host_threads()
-    n_clips = args.cpu_clips or max(threads * 32, 64)
-    kind, used, total = cpu_reference_run(n_clips, args.samples, threads, args.warmup, args.steps)
-    ch_samples = n_clips * 2 * args.samples
-    value = ch_samples * args.steps / total
+    n_clips = cpu_sample_clips(w, threads, args.cpu_clips)
+    kind, used, total = cpu_reference_run(w, n_clips, threads, args.warmup, args.steps)
+    value = n_clips * 2 * w["samples"] * args.steps / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, n_clips_note="reference arm renders a bounded sample of %d clips per step" % n_clips),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(w, name),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind,
-                         "sample": "%d drum-hit clips x 2 ch x %d samples per step, %s -> %s processBlock in %d-sample blocks, "
-                                   "%d host processes" % (n_clips, args.samples, CHAIN[0], CHAIN[1], BLOCK, used)},
+                         "sample": "each step renders a bounded sample of %d of the workload's %d clips (x 2 ch x %d samples) through %s "
+                                   "in %d-sample blocks on %d host processes" % (n_clips, w["clips"], w["samples"], " -> ".join(w["chain"]), BLOCK, used)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -235,72 +314,182 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config(args, n_clips_note=None):
-    cfg = {"workload": "configs[1]: JuicyPunch -> JuicyWidth chain on %d stereo drum-hit clips (1 s, 48 kHz) per GPU"
-                       % args.clips,
-           "chain": CHAIN, "clips_per_gpu": args.clips, "channels": 2, "samples_per_clip": args.samples,
-           "sample_rate": SAMPLE_RATE, "block_size": BLOCK, "parameters": "plugin defaults (program 0)",
-           "cache": "inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed"
-                    % (args.clips * 2 * args.samples * 4 / 1e9),
-           "sharding": "independent clips per rank, no data-path collective; one all_gather of per-clip records"}
-    if n_clips_note:
-        cfg["note"] = n_clips_note
-    return cfg
-
-
 # ---------------------------------------------------------------------------------------------- engine arm
 
-FULL_CHAIN = ["JuicyPunch", "JuicySaturator", "JuicyTexture", "JuicyWidth", "JuicyMotion", "JuicyCohere", "JuicyInfer"]
+class Bench:
+    """One workload on this rank's GPU: device-resident steps, end-to-end steps, clocks."""
 
+    def __init__(self, jb, torch, w, name, local, rank, world, stream, comm_id=None):
+        self.jb, self.torch, self.w, self.name = jb, torch, w, name
+        self.local, self.rank, self.world, self.stream = local, rank, world, stream
+        n_clips, n = w["clips"], w["samples"]
+        self.count = n_clips * 2 * n
+        self.d_in = torch.empty(self.count, dtype=torch.float32, device="cuda")
+        self.d_out = torch.empty(self.count, dtype=torch.float32, device="cuda")
+        jb.synth_fill_device(self.d_in.data_ptr(), w["synth"], rank * n_clips, n_clips, 2, n, SAMPLE_RATE, device=local,
+                             stream=stream.cuda_stream)
+        self.eng = jb.BatchProcessor(w["chain"], n_clips, device=local)
+        self.eng.set_stream(stream.cuda_stream)
+        if w["per_clip"]:
+            slot, pid, mod = w["per_clip"]
+            for c in range(n_clips):
+                self.eng.setParameterClips(pid, float((rank * n_clips + c) % mod), c, 1, slot)
+        self.eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+        self.last_slot = len(w["chain"]) - 1
+        self.d_gather = None
+        if world > 1:
+            L = jb.lib()
+            jb._check(L.jb_comm_init_rank(self.eng._h, comm_id, world, rank))
+            pitch = L.jb_record_pitch(self.eng._h)
+            self.d_gather = torch.empty(world * 16 * pitch, dtype=torch.float32, device="cuda")
+        # a single clip fits the L2: overwrite a buffer larger than the L2 between timed renders
+        self.flush = torch.empty(300 * 1024 * 1024, dtype=torch.float32, device="cuda") if self.count * 8 <= 4e8 else None
 
-def survey_other_configs(jb, device, peak_gbs):
-    """Device-resident renders of BASELINE.json configs[0], [2], [3] and one 8-GPU shard of [4] (SURVEY.md §8(d) shapes),
-    timed with the library's CUDA events around its kernel launches; 1 warm-up + 2 timed renders each."""
-    specs = [
-        ("configs[0] C1: JuicySaturator, 1 clip x 10 s sine sweep", ["JuicySaturator"], 1, 480000, "sweep", None),
-        ("configs[2] C3: JuicyTexture, 8192 stereo instances (16384 streams), impulse trains, material = clip mod 5",
-         ["JuicyTexture"], 8192, 48000, "impulse", ("material", 5)),
-        ("configs[3] C4: JuicyInfer scoring, 65536 clips (noise / sweep / impulse / drum mix)", ["JuicyInfer"], 65536, 48000, "mixed", None),
-        ("configs[4] C5: full 7-plugin chain, one GPU's shard of 262144 clips (32768)", FULL_CHAIN, 32768, 48000, "mixed", None),
-    ]
-    out = []
-    for name, chain, n_clips, n, synth, clipmod in specs:
-        try:
-            buf = jb.DeviceBuffer(n_clips * 2 * n * 4, device)
-            # the big configurations render in place (C4 is 25 GB of input); C3's five concurrent launches go out of place
-            dst = jb.DeviceBuffer(n_clips * 2 * n * 4, device) if clipmod else buf
-            jb.synth_fill_device(buf.ptr.value, synth, 0, n_clips, 2, n, SAMPLE_RATE, device=device, stream=0)
-            eng = jb.BatchProcessor(chain, n_clips, device=device)
-            if clipmod:
-                pid, k = clipmod
-                for c in range(n_clips):
-                    eng.setParameterClips(pid, float(c % k), c, 1, 0)
-            eng.prepareToPlay(SAMPLE_RATE, BLOCK)
-            eng.reset()
-            eng.process_device(buf.ptr.value, dst.ptr.value, n)
-            eng.synchronize()
-            eng.kernel_time_ms()
-            steps = 2
+    def step(self):
+        self.eng.reset()
+        if self.flush is not None:
+            self.flush.zero_()
+        self.eng.process_device(self.d_in.data_ptr(), self.d_out.data_ptr(), self.w["samples"])
+        if self.world > 1:
+            # per-clip records -> every rank (north_star: NCCL only to gather per-clip scores), issued by the library
+            self.jb._check(self.jb.lib().jb_gather_records(self.eng._h, self.last_slot, ctypes.c_void_p(self.d_gather.data_ptr())))
+
+    def timed(self, steps, warmup, barrier):
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                self.step()
+            torch.cuda.synchronize()
+            barrier()
+            self.eng.kernel_time_ms()
+            launches0 = self.jb.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(self.stream)
             for _ in range(steps):
-                eng.reset()
-                eng.process_device(buf.ptr.value, dst.ptr.value, n)
-            ms, launches = eng.kernel_time_ms()
-            ms /= steps
-            ch_samples = n_clips * 2 * n
-            read_only = chain == ["JuicyInfer"]
-            n_blocks = (n + BLOCK - 1) // BLOCK
-            alg = (4.0 if read_only else 8.0) * ch_samples + 64.0 * n_clips * n_blocks * len(chain)
-            out.append({"workload": name, "chain": chain, "clips": n_clips, "samples_per_clip": n, "ms_per_render": ms,
-                        "launches_per_render": launches / steps, "value": ch_samples / (ms / 1000.0), "unit": UNIT,
-                        "in_place": dst is buf, "algorithmic_bytes": alg, "frac_of_hbm_peak": alg / (ms / 1000.0) / 1e9 / peak_gbs,
-                        "math": "auto (fast: no resonant Texture material behind a shaper in these configurations)"})
-            eng.close()
-            if dst is not buf:
-                dst.free()
-            buf.free()
-        except Exception as exc:  # a survey line must never take the bench line down
-            out.append({"workload": name, "error": str(exc)})
-    return out
+                self.step()
+            e1.record(self.stream)
+            torch.cuda.synchronize()
+            barrier()
+            ms_total = e0.elapsed_time(e1)
+            kernel_ms, kernel_renders = self.eng.kernel_time_ms()
+            launches = self.jb.launch_count() - launches0
+            coop, lane = self.eng.path_launches()
+        if self.flush is not None:
+            # the flush is inside the event bracket: report the renders alone (library events around its launches)
+            ms_total = kernel_ms
+        return ms_total, kernel_ms, kernel_renders, launches, coop, lane
+
+    def e2e(self, steps, barrier):
+        """jb_process_host with pinned HOST buffers: H2D of the inputs and D2H of the results inside the timed region."""
+        jb, torch = self.jb, self.torch
+        n_clips, n = self.w["clips"], self.w["samples"]
+        h_in = jb.PinnedBuffer((n_clips, 2, n))
+        # big batches render in place on the host side too (h_out == h_in halves the pinned memory: 8 ranks x 12.6 GB)
+        in_place = self.count * 4 > 4e9
+        h_out = h_in if in_place else jb.PinnedBuffer((n_clips, 2, n))
+        jb._check(jb.lib().jb_copy_to_host(self.local, h_in.array.ctypes.data, self.d_in.data_ptr(), self.count * 4))
+        rec = None
+
+        def one():
+            self.eng.reset()
+            self.eng.process_host_ptr(h_in.array.ctypes.data, h_out.array.ctypes.data, n)
+            return self.eng.getLatestMetrics(self.last_slot)
+
+        one()
+        if in_place:  # the warm-up overwrote the input: restore it, so the timed steps render the same audio
+            jb._check(jb.lib().jb_copy_to_host(self.local, h_in.array.ctypes.data, self.d_in.data_ptr(), self.count * 4))
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            rec = one()
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        barrier()
+        h_in.free()
+        if h_out is not h_in:
+            h_out.free()
+        return secs, rec, in_place
+
+    def close(self):
+        try:
+            self.eng.close()
+        except Exception:
+            pass
+        self.d_in = self.d_out = self.d_gather = self.flush = None
+        self.torch.cuda.empty_cache()
+
+
+def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup, e2e_steps, comm_id, peak, peak_src,
+            with_fast=False):
+    """Device-resident + end-to-end measurement of one workload; returns the result dict on rank 0 (None elsewhere)."""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    b = Bench(jb, torch, w, name, local, rank, world, stream, comm_id)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, kernel_ms, kernel_renders, launches, coop, lane = b.timed(steps, warmup, barrier)
+    e2e_s, rec_host, e2e_in_place = b.e2e(e2e_steps, barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    fast = None
+    if with_fast and world == 1:
+        b.eng.set_math_mode("fast")
+        f_total, f_kernel, f_renders, _, _, _ = b.timed(max(2, steps // 2), 1, barrier)
+        b.eng.set_math_mode("auto")
+        fast = {"ms_per_step": f_total / max(2, steps // 2), "mean_render_ms": f_kernel / max(f_renders, 1)}
+    times = torch.tensor([ms_total, e2e_s * 1000.0, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, kernel_ms = [float(x) for x in times.tolist()]
+    b.close()
+    if rank != 0:
+        return None
+    ch_samples_rank = w["clips"] * 2 * w["samples"]
+    value = world * ch_samples_rank * steps / (ms_total / 1000.0)
+    e2e_value = world * ch_samples_rank * e2e_steps / (e2e_ms / 1000.0)
+    alg = algorithmic_bytes(w)
+    mean_render_ms = kernel_ms / max(kernel_renders, 1)
+    achieved = alg / (mean_render_ms / 1000.0) / 1e9
+    kernels_per_render = launches / max(kernel_renders, 1)
+    if coop >= lane and coop > 0:
+        kernel_name = "jb_coop_kernel"
+    elif len(w["chain"]) == 1 and not w["per_clip"]:
+        kernel_name = "jb_single_kernel / jb_pair_kernel (%s)" % w["chain"][0]
+    else:
+        kernel_name = "render = %.0f kernel launches (one per plugin / parameter set)" % kernels_per_render
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            entry = tj.get(name) if isinstance(tj.get(name), dict) else (tj if tj.get("kernel") == kernel_name else None)
+            traffic = entry.get("bytes_per_launch") if entry else None
+        except Exception:
+            traffic = None
+    count_bytes = ch_samples_rank * 4
+    res = {
+        "value": value, "unit": UNIT, "ms_per_step": ms_total / steps, "steps": steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_launch": alg,
+                     "mean_launch_ms": mean_render_ms, "launches_timed": kernel_renders, "peak_source": peak_src,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": count_bytes, "d2h_bytes_per_step": count_bytes + 64 * w["clips"],
+                "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "host_in_place": e2e_in_place,
+                "api": "jb_process_host + jb_get_metrics (pinned host buffers)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "math": "auto (exact tanh / pow where a Punch / Saturator feeds another plugin)",
+        "mean_juiciness": float(np.mean(rec_host[:, 13])) if rec_host is not None else None,
+    }
+    if fast:
+        res["fast_math"] = {"ms_per_step": fast["ms_per_step"], "value": ch_samples_rank / (fast["ms_per_step"] / 1000.0),
+                            "mean_render_ms": fast["mean_render_ms"],
+                            "frac": alg / (fast["mean_render_ms"] / 1000.0) / 1e9 / peak,
+                            "note": "jb_set_math_mode(JB_MATH_FAST): MUFU-based tanh / pow, not decision-safe for every clip"}
+    return res
 
 
 def run_engine_arm(args):
@@ -317,6 +506,8 @@ def run_engine_arm(args):
     torch.cuda.set_device(local)
     all_cpus = bind_to_gpu_numa_node(local)
     stdout_fd = None
+    jb = load_juicy_batch()
+    comm_id = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version (the image sets NCCL_DEBUG=VERSION) and any debug lines on fd 1; the contract is ONE JSON
@@ -325,157 +516,54 @@ def run_engine_arm(args):
         stdout_fd = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    jb = load_juicy_batch()
-    sharding = load_sharding()
-    n_clips, n = args.clips, args.samples
-    count = n_clips * 2 * n
-    d_in = torch.empty(count, dtype=torch.float32, device="cuda")
-    d_out = torch.empty(count, dtype=torch.float32, device="cuda")
-    stream = torch.cuda.Stream()
-    jb.synth_fill_device(d_in.data_ptr(), "drum", rank * n_clips, n_clips, 2, n, SAMPLE_RATE, device=local,
-                         stream=stream.cuda_stream)
-    eng = jb.BatchProcessor(CHAIN, n_clips, device=local)
-    eng.set_stream(stream.cuda_stream)
-    eng.prepareToPlay(SAMPLE_RATE, BLOCK)
-    last_slot = len(CHAIN) - 1
-    rec_bytes = 16 * 4 * n_clips
-    # device view of the engine's SoA metrics record [16][clipPitch] for the gather
-    pitch = sharding.clip_pitch(n_clips)
-
-    class _DeviceView:  # zero-copy torch view of the engine's record block (plumbing for the NCCL gather)
-        __cuda_array_interface__ = {"shape": (16 * pitch,), "typestr": "<f4", "version": 2,
-                                    "data": (eng.metrics_device_ptr(last_slot), False)}
-
-    local_rec = torch.as_tensor(_DeviceView(), device="cuda")
-    first_clip, _ = sharding.shard_range(world * n_clips, rank, world)  # weak scaling: n_clips per rank
-    assert first_clip == rank * n_clips
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def step():
-        eng.reset()
-        eng.process_device(d_in.data_ptr(), d_out.data_ptr(), n)
-        if world > 1:
-            # per-clip records -> every rank (north_star: NCCL only to gather per-clip scores)
-            sharding.gather_records(local_rec, world, dist)
-
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step()
-        torch.cuda.synchronize()
-        barrier()
-        eng.kernel_time_ms()
-        launches0 = jb.launch_count()
-        sampler = ClockSampler(local)
+        # the library's own communicator for the score gather: rank 0 makes the id, torch.distributed carries the 128 bytes
+        idbuf = ctypes.create_string_buffer(128)
         if rank == 0:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        barrier()
-        ms_total = e0.elapsed_time(e1)
-        kernel_ms, kernel_launches = eng.kernel_time_ms()
-        launches = jb.launch_count() - launches0
-        coop_launches, lane_launches = eng.path_launches()
-        kernel_name = "jb_coop_kernel" if coop_launches >= lane_launches else "jb_process_kernel"
+            jb._check(jb.lib().jb_comm_unique_id(idbuf))
+        t = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        comm_id = bytes(t.cpu().tolist())
 
-        # ---- end to end through the C ABI with pinned host buffers
-        h_in = jb.PinnedBuffer((n_clips, 2, n))
-        h_out = jb.PinnedBuffer((n_clips, 2, n))
-        jb._check(jb.lib().jb_copy_to_host(local, h_in.array.ctypes.data, d_in.data_ptr(), count * 4))
-        rec_host = None
-
-        def e2e_step():
-            eng.reset()
-            eng.process_host_ptr(h_in.array.ctypes.data, h_out.array.ctypes.data, n)
-            return eng.getLatestMetrics(last_slot)
-
-        e2e_step()
-        torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            rec_host = e2e_step()
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        barrier()
-        clocks = sampler.stop() if rank == 0 else None
-
-    times = torch.tensor([ms_total, e2e_s * 1000.0, kernel_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, kernel_ms_max = [float(x) for x in times.tolist()]
-
-    ch_samples_rank = n_clips * 2 * n
-    value = world * ch_samples_rank * args.steps / (ms_total / 1000.0)
-    e2e_value = world * ch_samples_rank * args.steps / (e2e_ms / 1000.0)
-
-    # roofline of the render kernel: 8 B per channel-sample (4 read + 4 written) plus one 64 B
-    # record per (clip, block, plugin)
-    n_blocks = (n + BLOCK - 1) // BLOCK
-    alg_bytes = 8.0 * ch_samples_rank + 64.0 * n_clips * n_blocks * len(CHAIN)
+    name, w = pick_workload(args, world)
+    stream = torch.cuda.Stream()
     peak, peak_src = measured_peak_gbs()
-    mean_launch_ms = kernel_ms / max(kernel_launches, 1)
-    achieved = alg_bytes / (mean_launch_ms / 1000.0) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            traffic = tj.get("bytes_per_launch") if tj.get("kernel") == kernel_name else None
-        except Exception:
-            traffic = None
+    e2e_steps = max(1, min(args.steps, 5 if w["clips"] * w["samples"] > 1e9 else args.steps))
+    res = measure(jb, torch, dist, w, name, local, rank, world, stream, args.steps, args.warmup, e2e_steps, comm_id, peak, peak_src,
+                  with_fast=True)
 
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_launch": alg_bytes,
-                         "mean_launch_ms": mean_launch_ms, "launches_timed": kernel_launches, "peak_source": peak_src,
-                         "frac_of_nominal_8TBs": achieved / 8000.0},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": count * 4,
-                    "d2h_bytes_per_step": count * 4 + rec_bytes, "ms_per_step": e2e_ms / args.steps,
-                    "api": "jb_process_host + jb_get_metrics (pinned host buffers)"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "mean_juiciness": float(np.mean(rec_host[:, 13])) if rec_host is not None else None,
-        }
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(w, name)}
+        for k in ("roofline", "e2e", "gpu_launches", "clocks", "math", "mean_juiciness", "fast_math"):
+            if k in res:
+                line[k] = res[k]
         if world == 1 and not args.no_cpu:
             if all_cpus:
                 os.sched_setaffinity(0, all_cpus)  # the CPU leg uses every host core again
-            threads = host_threads()
-            cpu_clips = args.cpu_clips or max(threads * 32, 64)
-            kind, used, secs = cpu_reference_run(cpu_clips, n, threads, 1, 2)
-            line["cpu_baseline"] = {
-                "value": 2 * cpu_clips * 2 * n / secs, "unit": UNIT, "cores": used, "kind": kind,
-                "sample": "%d of the %d drum-hit clips (x 2 ch x %d samples), 2 passes, %d host processes"
-                          % (cpu_clips, n_clips, n, used)}
-        if world == 1 and not args.no_survey:
-            # the other BASELINE.json configurations, device resident, one GPU (explanatory: the bench line above is
-            # configs[1]); freed first: C4 alone holds 25 GB of input
-            eng.close()
-            del d_in, d_out, local_rec
-            torch.cuda.empty_cache()
-            line["other_configs"] = survey_other_configs(jb, local, peak)
+            line["cpu_baseline"] = cpu_baseline(w, host_threads(), args.cpu_clips)
+        if world == 1 and not args.no_survey and not args.config:
+            # the other BASELINE.json configurations on this GPU, each measured like the headline (fewer steps)
+            others = []
+            for other in ("C1", "C3", "C4", "C5"):
+                ow = dict(WORKLOADS[other])
+                try:
+                    r = measure(jb, torch, dist, ow, other, local, 0, 1, stream, 3, 3, 2, None, peak, peak_src, with_fast=(other == "C5"))
+                    r["config"] = workload_config(ow, other)
+                    if not args.no_cpu:
+                        r["cpu_baseline"] = cpu_baseline(ow, host_threads(), 0)
+                        r["e2e_vs_cpu"] = r["e2e"]["value"] / r["cpu_baseline"]["value"]
+                    others.append(r)
+                except Exception as exc:  # a survey line must never take the bench line down
+                    others.append({"config": workload_config(ow, other), "error": repr(exc)})
+            line["other_configs"] = others
         if stdout_fd is not None:
             sys.stdout.flush()
             os.dup2(stdout_fd, 1)
         print(json.dumps(line))
         sys.stdout.flush()
-    try:
-        eng.close()
-    except Exception:
-        pass
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -486,10 +574,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("engine", "reference"), default="engine")
-    ap.add_argument("--clips", type=int, default=4096, help="clips per GPU (BASELINE.json configs[1]: 4096)")
-    ap.add_argument("--samples", type=int, default=48000, help="samples per clip (1 s at 48 kHz)")
-    ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU sample (default 4 per host thread)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", choices=sorted(WORKLOADS), default=None,
+                    help="workload (default: C2 = BASELINE.json configs[1] at N = 1, C5 = configs[4] per GPU at N > 1)")
+    ap.add_argument("--clips", type=int, default=0, help="override the clips per GPU of the workload")
+    ap.add_argument("--samples", type=int, default=0, help="override the samples per clip of the workload")
+    ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU sample (default: ~4 M channel-samples per host thread)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-survey", action="store_true", help="skip the other_configs survey (N = 1 only)")
     ap.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -236,14 +236,48 @@ int jb_set_path(jb_engine* e, int mode);
  * PluginProcessor.cpp:100,106).  JB_MATH_FAST: special-function-unit based, within 3e-6 relative of the C library (the
  * stated sample tolerance for the plugin itself).  JB_MATH_EXACT: the C library's own algorithms restated (fdlibm tanhf,
  * glibc powf), bit-identical to the reference built against glibc 2.28 - 2.39, about 1.5x the arithmetic.  JB_MATH_AUTO
- * (default): exact when a JuicyTexture comes later in the chain -- its metal / wood / plastic resonators amplify a 1e-6
- * input difference ~200x -- fast otherwise.  The cooperative kernel only runs in fast mode. */
+ * (default): see DESIGN.md §4.4 for the rule -- exact wherever a later plugin of the chain would amplify or threshold
+ * the shaper's last-bit differences, fast otherwise.  Mono and stereo buses honour the mode alike.  The cooperative
+ * kernel only runs in fast mode. */
 #define JB_MATH_AUTO 0
 #define JB_MATH_EXACT 1
 #define JB_MATH_FAST 2
 int jb_set_math_mode(jb_engine* e, int mode);
 /* Launches of each render kernel by this engine so far (either pointer may be null). */
 int jb_path_launches(const jb_engine* e, long long* cooperative, long long* lane_per_clip);
+
+/* ---- Sharding across the GPUs of one box and the score gather ------------------------------------
+ * The reference has no counterpart: a DAW runs one plugin instance per track and instances share no state
+ * (all state is instance members, e.g. JuicyTexture/PluginProcessor.h:79-81).  That independence is the sharding
+ * axis: rank r of N owns the contiguous clip range jb_shard_range gives it, renders it with its own engine, and
+ * nothing is exchanged while rendering.  The ONE collective is an ncclAllGather of the per-clip records
+ * (`getLatestMetrics()` of every instance, 16 floats per clip) after the render, over NVLink / NVSwitch.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2"; JB_NCCL_LIB overrides): hosts that never shard never need it.
+ *
+ *   multi-process (one process per GPU):  rank 0 calls jb_comm_unique_id and hands the 128 bytes to the others
+ *       (any channel the launcher has); every rank calls jb_comm_init_rank(engine, id, N, rank).
+ *   single process driving N engines on N distinct GPUs:  jb_comm_init_all(engines, N).
+ */
+#define JB_COMM_ID_BYTES 128
+/* [first, first + count) of the clips rank `rank` of `world` renders: contiguous, balanced to within one clip. */
+int jb_shard_range(long long n_clips, int rank, int world, long long* first, long long* count);
+/* Clips per field in the engine's structure-of-arrays record block (n_clips rounded up to 32). */
+long long jb_record_pitch(const jb_engine* e);
+int jb_comm_version(int* nccl_version);
+int jb_comm_unique_id(void* id_out /* JB_COMM_ID_BYTES */);
+int jb_comm_init_rank(jb_engine* e, const void* id, int n_ranks, int rank);
+int jb_comm_init_all(jb_engine* const* engines, int n_engines);
+int jb_comm_destroy(jb_engine* e);
+int jb_comm_size(const jb_engine* e);
+int jb_comm_rank(const jb_engine* e);
+/* ncclAllGather of plugin `slot`'s latest records on the engine's stream (asynchronous): every rank's block
+ * [16][jb_record_pitch] (what jb_metrics_device points at) -> d_out[rank][16][pitch] on every rank.  All engines of a
+ * communicator must hold the same number of clips. */
+int jb_gather_records(jb_engine* e, int slot, float* d_out);
+/* The same for a single process that drives all engines of the communicator (grouped NCCL calls). */
+int jb_gather_records_all(jb_engine* const* engines, int n_engines, int slot, float* const* d_out);
+/* Gather + download + unpack: out[rank * clips_per_rank + clip], jb_metrics records in global clip order. */
+int jb_gather_records_host(jb_engine* e, int slot, jb_metrics* out, int clips_per_rank);
 
 /* Number of kernel launches issued by this library since load (bench evidence). */
 long long jb_launch_count(void);

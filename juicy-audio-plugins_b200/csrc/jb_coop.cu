@@ -25,6 +25,7 @@
 //
 // Reference lines are cited per routine, relative to /root/reference.
 #include "jb_device.cuh"
+#include "jb_libm.h"
 
 #include <stdint.h>
 #include <stdio.h>
@@ -175,6 +176,10 @@ __device__ __forceinline__ Cursor cursor_next(const ProcArgs& a, const Cursor& c
 
 // JuicyPunch/PluginProcessor.cpp:94-110 on one channel's chunk, restarting the two linear
 // envelopes from the scout's checkpoint (same operand order as the scout => same bits).
+// EXACT: the C library's own pow / tanh (jb_libm.h) and the reference's unfused operand order throughout, so the
+// samples are the reference's bit for bit (ProcArgs::exactMath: something downstream thresholds or amplifies them);
+// otherwise the MUFU-based routines and fused multiply-adds in the pointwise part (within 3e-6 of clip peak).
+template <bool EXACT>
 __device__ __forceinline__ void punch_chunk(float (&x)[CO_CH], float2 ck, const PunchCoef& c)
 {
     float fEnv = ck.x, sEnv = ck.y;
@@ -185,16 +190,27 @@ __device__ __forceinline__ void punch_chunk(float (&x)[CO_CH], float2 ck, const 
         const float adry = fabsf(dry);
         fEnv = c.omFast * adry + c.fastCoeff * fEnv;
         sEnv = c.omSlow * adry + c.slowCoeff * sEnv;
-        // from here on pointwise: fused multiply-adds (1e-7 relative, inside the sample tolerance)
         const float transient = jmaxf(0.0f, fEnv - sEnv);
-        const float transientCurve = pow_unit(transient, c.curveExp);
-        const float punchGain = fmaf(c.punchK, transientCurve, 1.0f);
-        const float sustainGain = fmaf(c.sustainK, jmaxf(0.0f, fmaf(-0.6f, transient, sEnv)), 1.0f);
-        float wet = dry * punchGain * sustainGain;
-        const float soft = tanh_fast(wet * c.drive) * invTanhDrive;
-        const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
-        wet = fmaf(c.clipAmt, hard - soft, soft);
-        x[i] = fmaf(c.mix, wet - dry, dry) * c.outGain;
+        if (EXACT) {
+            const float transientCurve = jblibm::powf_glibc_pos(transient, c.curveExp);
+            const float punchGain = 1.0f + c.punchK * transientCurve;
+            const float sustainGain = 1.0f + c.sustainK * jmaxf(0.0f, sEnv - transient * 0.6f);
+            float wet = dry * punchGain * sustainGain;
+            const float soft = jblibm::fdiv(jblibm::tanhf_fdlibm(wet * c.drive), c.tanhDrive);
+            const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
+            wet = soft + c.clipAmt * (hard - soft);
+            x[i] = (dry + c.mix * (wet - dry)) * c.outGain;
+        } else {
+            // from here on pointwise: fused multiply-adds (1e-7 relative, inside the sample tolerance)
+            const float transientCurve = pow_unit(transient, c.curveExp);
+            const float punchGain = fmaf(c.punchK, transientCurve, 1.0f);
+            const float sustainGain = fmaf(c.sustainK, jmaxf(0.0f, fmaf(-0.6f, transient, sEnv)), 1.0f);
+            float wet = dry * punchGain * sustainGain;
+            const float soft = tanh_fast(wet * c.drive) * invTanhDrive;
+            const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
+            wet = fmaf(c.clipAmt, hard - soft, soft);
+            x[i] = fmaf(c.mix, wet - dry, dry) * c.outGain;
+        }
     }
 }
 
@@ -230,6 +246,7 @@ __device__ __forceinline__ WidthPrefetch width_prefetch(const WidthCoef& c, cons
     }
     return pf;
 }
+template <bool EXACT>
 __device__ __forceinline__ void width_chunk(float (&l)[CO_CH], float (&r)[CO_CH], const WidthCoef& c, const float* tab,
                                             int kStart, int& warpTotal, float* ring, int wpos0, int lane, int nValid,
                                             const WidthPrefetch& pf)
@@ -314,8 +331,13 @@ __device__ __forceinline__ void width_chunk(float (&l)[CO_CH], float (&r)[CO_CH]
 #pragma unroll
     for (int i = 0; i < CO_CH; ++i) {
         const float dryL = l[i], dryR = r[i];
-        l[i] = fmaf(c.mix, wetL[i] - dryL, dryL) * c.outGain;
-        r[i] = fmaf(c.mix, wetR[i] - dryR, dryR) * c.outGain;
+        if (EXACT) { // the reference's two roundings (JuicyWidth/PluginProcessor.cpp:134-135)
+            l[i] = (dryL + c.mix * (wetL[i] - dryL)) * c.outGain;
+            r[i] = (dryR + c.mix * (wetR[i] - dryR)) * c.outGain;
+        } else {
+            l[i] = fmaf(c.mix, wetL[i] - dryL, dryL) * c.outGain;
+            r[i] = fmaf(c.mix, wetR[i] - dryR, dryR) * c.outGain;
+        }
     }
 }
 
@@ -605,6 +627,7 @@ struct CoopArgs {
     int debugSkip;      // profiling builds (-DJB_COOP_DEBUG, JB_COOP_DEBUG_SKIP): bit 0 envelope walk, 1 band walk, 2 bulk math, 3 scout
 };
 
+template <bool EXACT>
 __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_constant__ CoopArgs ca)
 {
     extern __shared__ __align__(1024) unsigned char smemRaw[];
@@ -852,15 +875,15 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                         const SlotDesc& d = a.slot[s];
                         if (d.kind == K_PUNCH) {
                             const float2 zero = make_float2(0.0f, 0.0f); // lanes past the step's end have no checkpoint
-                            punch_chunk(l, nValid > 0 ? sm.ckpt[slot][2 * ci][lane] : zero, d.c.punch);
-                            punch_chunk(r, nValid > 0 ? sm.ckpt[slot][2 * ci + 1][lane] : zero, d.c.punch);
+                            punch_chunk<EXACT>(l, nValid > 0 ? sm.ckpt[slot][2 * ci][lane] : zero, d.c.punch);
+                            punch_chunk<EXACT>(r, nValid > 0 ? sm.ckpt[slot][2 * ci + 1][lane] : zero, d.c.punch);
                         } else if (d.kind == K_WIDTH) {
                             int total = 0;
                             const int kStart = firstStep ? 0 : sm.widthCount[ci];
                             const int wpos0 = sm.widthPos[ci];
                             __syncwarp();
                             float* ring = a.widthRing + (long long) (clip0 + ci) * a.ringClipStride;
-                            width_chunk(l, r, d.c.width, sm.widthTab, kStart, total, ring, wpos0, lane, nValid, widthPf);
+                            width_chunk<EXACT>(l, r, d.c.width, sm.widthTab, kStart, total, ring, wpos0, lane, nValid, widthPf);
                             if (lane == 0) {
                                 sm.widthCount[ci] = kStart + total;
                                 int np = wpos0 + cur.n;
@@ -974,8 +997,9 @@ int jbk_launch_coop(const ProcArgs* args, float* monoScratch, int numSMs, void* 
 {
     if (args->nClips <= 0 || args->nSamples <= 0)
         return 0;
-    {
-        cudaError_t e = cudaFuncSetAttribute(jb_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CoopSmem));
+    for (int v = 0; v < 2; ++v) {
+        cudaError_t e = v ? cudaFuncSetAttribute(jb_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CoopSmem))
+                          : cudaFuncSetAttribute(jb_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CoopSmem));
         if (e != cudaSuccess) {
             snprintf(g_coopErr, sizeof g_coopErr, "cudaFuncSetAttribute(jb_coop_kernel): %s", cudaGetErrorString(e));
             return -1;
@@ -996,7 +1020,10 @@ int jbk_launch_coop(const ProcArgs* args, float* monoScratch, int numSMs, void* 
     ca.debugSkip = 0;
 #endif
     const int grid = ca.numGroups < numSMs ? ca.numGroups : numSMs;
-    jb_coop_kernel<<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
+    if (args->exactMath)
+        jb_coop_kernel<true><<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
+    else
+        jb_coop_kernel<false><<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
     jbk_note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

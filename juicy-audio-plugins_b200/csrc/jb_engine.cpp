@@ -134,6 +134,12 @@ struct jb_engine {
     std::vector<cudaEvent_t> pipeEvents; // [plugin][segment] of a pipelined chain render
     int pipelineMaxClips = 16384;        // chains of at most this many clips are pipelined across plugins
 
+    // Score gather across the GPUs of one box: an NCCL communicator, opaque here (jb_comm_* below)
+    void* comm = nullptr;
+    int commRanks = 0, commRank = -1;
+    float* dGather = nullptr;      // [commRanks][JBK_REC][clipPitch] scratch of jb_gather_records_host
+    size_t gatherBytes = 0;
+
     // CUDA-event pairs around every render-kernel launch (jb_kernel_time_ms)
     std::vector<cudaEvent_t> timingEvents; // start0, stop0, start1, stop1, ...
     size_t timingUsed = 0;
@@ -180,6 +186,9 @@ void freeDevice(jb_engine* e)
     cudaFree(e->dCoopScratch);
     cudaFree(e->dClipMap);
     e->dClipMap = nullptr;
+    cudaFree(e->dGather);
+    e->dGather = nullptr;
+    e->gatherBytes = 0;
     for (int i = 0; i < jb_engine::kGroupStreams; ++i) {
         if (e->groupStream[i]) cudaStreamDestroy(e->groupStream[i]);
         if (e->groupJoin[i]) cudaEventDestroy(e->groupJoin[i]);
@@ -358,25 +367,22 @@ int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params
             if (k == jb::kPunch || k == jb::kTexture || k == jb::kMotion)
                 a.octets = 0;
     }
-    {   // Saturator / Punch transcendentals: the MUFU-based ones are within 3e-6 of the reference, which Texture's metal /
-        // wood / plastic resonators amplify ~200x; with a Texture further down the chain they run the C library's own
-        // algorithms (jb_libm.h) so that its input is the reference's, bit for bit.
-        // Which materials: measured on the full chain (profiles/r01_s6_chain_sensitivity.txt) gel and flesh stay at 1e-6 of
-        // clip peak with the fast routines (their mass-spring models are heavily damped), metal / wood / plastic reach
-        // 4e-5 .. 4e-3 -- so only a Texture whose material is one of those three asks for the exact routines.  Decided per
-        // launch from the parameter set being rendered (per-clip sets and automation each get their own answer).
-        bool shaperSeen = false, resonatorAfterShaper = false;
-        for (size_t s2 = 0; s2 < e->chain.size(); ++s2) {
-            const int k = e->chain[s2];
-            if (k == jb::kPunch || k == jb::kSaturator)
-                shaperSeen = true;
-            if (k == jb::kTexture && shaperSeen) {
-                const int material = (int) params[s2].raw("material");
-                if (material >= 1 && material <= 3)
-                    resonatorAfterShaper = true;
-            }
-        }
-        a.exactMath = e->mathMode == 1 || (e->mathMode == 0 && resonatorAfterShaper) ? 1 : 0;
+    {   // Saturator / Punch transcendentals (JB_MATH_AUTO).  The MUFU-based tanh / pow are within 3e-6 of the reference --
+        // inside the sample tolerance for the shaper's own output, but not once another plugin consumes that output:
+        //   * Texture's metal / wood / plastic resonators amplify an input difference ~200x (profiles/r01_s6_chain_sensitivity.txt);
+        //   * Width's `if (corrProxy < -0.1f) width *= dynamicLimit` (JuicyWidth/PluginProcessor.cpp:109-112), Motion's onset
+        //     detector (JuicyMotion/PluginProcessor.cpp:75-95) and every later analyzer's onset threshold
+        //     (JuicinessAnalyzer.cpp:69-75) are DISCONTINUOUS in their input: a last-bit difference flips a decision once in
+        //     ~10^8 samples, and a flipped Width decision moves the rest of the block by ~2e-2 of peak.  Measured at full
+        //     population (profiles/r02_parity_population.json): Saturator -> Width, fast math, 3 of 8192 mixed clips out of
+        //     tolerance; the 7-plugin chain, 5 of 32768; with the exact routines 0 of 32768 (bit-identical samples).
+        // So: a shaper with ANY plugin behind it runs the C library's own algorithms (jb_libm.h) and feeds its successor the
+        // reference's bits; a shaper that ends the chain (or stands alone) keeps the fast routines.  Decided per launch.
+        bool shaperFeedsPlugin = false;
+        for (size_t s2 = 0; s2 + 1 < e->chain.size(); ++s2)
+            if (e->chain[s2] == jb::kPunch || e->chain[s2] == jb::kSaturator)
+                shaperFeedsPlugin = true;
+        a.exactMath = e->mathMode == 1 || (e->mathMode == 0 && shaperFeedsPlugin) ? 1 : 0;
     }
     if (e->chain.size() == 1)
         a.octets = octetsFor(e->chain[0], nClips, nSamples, false, a.exactMath != 0);
@@ -458,7 +464,7 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
 {
     // Path choice: the cooperative (time-parallel) kernel when the chain and the call's shape allow it and
     // the batch is too small to fill the GPU with one lane per clip; the lane-per-clip kernels otherwise.
-    bool coop = allowCoop && a.exactMath == 0 && a.nCh == 2 && e->coopCapable && e->dCoopScratch != nullptr && jbk_coop_supported(&a) != 0;
+    bool coop = allowCoop && a.nCh == 2 && e->coopCapable && e->dCoopScratch != nullptr && jbk_coop_supported(&a) != 0;
     if (e->pathMode == 1)
         coop = false;
     else if (e->pathMode == 2 && !coop)
@@ -870,6 +876,8 @@ int jb_destroy(jb_engine* e)
 {
     if (e == nullptr)
         return JB_OK;
+    if (e->comm != nullptr)
+        jb_comm_destroy(e);
     freeDevice(e);
     delete e;
     return JB_OK;
@@ -1649,6 +1657,279 @@ int jb_synth_fill(float* d_audio, int kind, long long first_clip, int n_clips, i
     JB_CUDA(cudaSetDevice(device));
     if (jbk_launch_synth(d_audio, kind, first_clip, n_clips, n_channels, n_samples, sample_rate, seed, cuda_stream) != 0)
         return fail(JB_ERR_CUDA, "%s", jbk_last_cuda_error());
+    return JB_OK;
+}
+
+// ---------------------------------------------------------------- clip sharding and the NCCL score gather
+// Clips are independent plugin-instance chains: rank r of N renders a contiguous clip range with its own engine and
+// nothing is exchanged while rendering.  The one collective is ncclAllGather of the per-clip records after the render.
+// NCCL is resolved at run time (dlopen) so the library itself has no link-time dependency on it: a host that never
+// shards never needs it.  JB_NCCL_LIB overrides the library name; a process that already holds NCCL (e.g. one that
+// imported torch) gets that copy.
+} // extern "C"
+
+#include <dlfcn.h>
+
+namespace {
+
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+    void* handle = nullptr;
+    std::string error;
+};
+constexpr int kNcclFloat32 = 7; // ncclFloat32 (nccl.h: ncclDataType_t)
+
+NcclApi* ncclApi()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried)
+        return api.handle ? &api : nullptr;
+    tried = true;
+    const char* names[] = { std::getenv("JB_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names) {
+        if (n == nullptr || *n == 0)
+            continue;
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle)
+            break;
+        api.error = dlerror();
+    }
+    if (!api.handle)
+        return nullptr;
+    bool ok = true;
+    auto sym = [&](const char* name) { void* p = dlsym(api.handle, name); ok = ok && p != nullptr; return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+    if (!ok) {
+        api.error = "a required nccl* symbol is missing";
+        dlclose(api.handle);
+        api.handle = nullptr;
+        return nullptr;
+    }
+    return &api;
+}
+
+int needNccl(NcclApi** out)
+{
+    *out = ncclApi();
+    if (*out == nullptr)
+        return fail(JB_ERR_UNSUPPORTED, "NCCL is not available (dlopen libnccl.so.2 failed; set JB_NCCL_LIB)");
+    return JB_OK;
+}
+
+#define JB_NCCL(api, call)                                                                              \
+    do {                                                                                                \
+        const int rc__ = (call);                                                                        \
+        if (rc__ != 0)                                                                                  \
+            return fail(JB_ERR_CUDA, "%s failed: %s", #call, (api)->GetErrorString(rc__));              \
+    } while (0)
+
+} // namespace
+
+extern "C" {
+
+int jb_shard_range(long long n_clips, int rank, int world, long long* first, long long* count)
+{
+    if (n_clips < 0 || world < 1 || rank < 0 || rank >= world || first == nullptr || count == nullptr)
+        return fail(JB_ERR_ARG, "jb_shard_range: rank %d of %d, %lld clips", rank, world, n_clips);
+    const long long base = n_clips / world, extra = n_clips % world;
+    *first = rank * base + std::min<long long>(rank, extra);
+    *count = base + (rank < extra ? 1 : 0);
+    return JB_OK;
+}
+
+long long jb_record_pitch(const jb_engine* e) { return e ? e->clipPitch : 0; }
+
+int jb_comm_version(int* version)
+{
+    NcclApi* api = nullptr;
+    if (int rc = needNccl(&api))
+        return rc;
+    if (version == nullptr)
+        return fail(JB_ERR_ARG, "jb_comm_version: null output");
+    JB_NCCL(api, api->GetVersion(version));
+    return JB_OK;
+}
+
+int jb_comm_unique_id(void* id_out)
+{
+    NcclApi* api = nullptr;
+    if (int rc = needNccl(&api))
+        return rc;
+    if (id_out == nullptr)
+        return fail(JB_ERR_ARG, "jb_comm_unique_id: null output");
+    NcclApi::UniqueId id;
+    JB_NCCL(api, api->GetUniqueId(&id));
+    std::memcpy(id_out, &id, sizeof id);
+    return JB_OK;
+}
+
+int jb_comm_init_rank(jb_engine* e, const void* id, int n_ranks, int rank)
+{
+    if (int rc = checkEngine(e))
+        return rc;
+    if (int rc = setDevice(e))
+        return rc;
+    NcclApi* api = nullptr;
+    if (int rc = needNccl(&api))
+        return rc;
+    if (id == nullptr || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return fail(JB_ERR_ARG, "jb_comm_init_rank: rank %d of %d", rank, n_ranks);
+    if (e->comm != nullptr)
+        return fail(JB_ERR_STATE, "jb_comm_init_rank: this engine already has a communicator");
+    NcclApi::UniqueId uid;
+    std::memcpy(&uid, id, sizeof uid);
+    JB_NCCL(api, api->CommInitRank(&e->comm, n_ranks, uid, rank));
+    e->commRanks = n_ranks;
+    e->commRank = rank;
+    return JB_OK;
+}
+
+int jb_comm_init_all(jb_engine* const* engines, int n)
+{
+    if (engines == nullptr || n < 1)
+        return fail(JB_ERR_ARG, "jb_comm_init_all: no engines");
+    NcclApi* api = nullptr;
+    if (int rc = needNccl(&api))
+        return rc;
+    std::vector<int> devs;
+    for (int i = 0; i < n; ++i) {
+        if (int rc = checkEngine(engines[i]))
+            return rc;
+        if (engines[i]->hostOnly)
+            return fail(JB_ERR_CUDA, "jb_comm_init_all: engine %d has no device", i);
+        if (engines[i]->comm != nullptr)
+            return fail(JB_ERR_STATE, "jb_comm_init_all: engine %d already has a communicator", i);
+        if (std::find(devs.begin(), devs.end(), engines[i]->device) != devs.end())
+            return fail(JB_ERR_ARG, "jb_comm_init_all: two engines share device %d (one engine per GPU)", engines[i]->device);
+        devs.push_back(engines[i]->device);
+    }
+    std::vector<void*> comms((size_t) n, nullptr);
+    JB_NCCL(api, api->CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; ++i) {
+        engines[i]->comm = comms[(size_t) i];
+        engines[i]->commRanks = n;
+        engines[i]->commRank = i;
+    }
+    return JB_OK;
+}
+
+int jb_comm_destroy(jb_engine* e)
+{
+    if (int rc = checkEngine(e))
+        return rc;
+    if (e->comm == nullptr)
+        return JB_OK;
+    NcclApi* api = nullptr;
+    if (int rc = needNccl(&api))
+        return rc;
+    if (int rc = setDevice(e))
+        return rc;
+    cudaStreamSynchronize(e->stream);
+    api->CommDestroy(e->comm);
+    e->comm = nullptr;
+    e->commRanks = 0;
+    e->commRank = -1;
+    return JB_OK;
+}
+
+int jb_comm_size(const jb_engine* e) { return e ? e->commRanks : 0; }
+int jb_comm_rank(const jb_engine* e) { return e ? e->commRank : -1; }
+
+int jb_gather_records(jb_engine* e, int slot, float* d_out)
+{
+    if (int rc = checkSlot(e, slot))
+        return rc;
+    if (int rc = setDevice(e))
+        return rc;
+    if (e->comm == nullptr)
+        return fail(JB_ERR_STATE, "jb_gather_records: no communicator (jb_comm_init_rank / jb_comm_init_all)");
+    if (!e->prepared)
+        return fail(JB_ERR_STATE, "jb_gather_records before jb_prepare");
+    if (d_out == nullptr)
+        return fail(JB_ERR_ARG, "jb_gather_records: null output");
+    NcclApi* api = nullptr;
+    if (int rc = needNccl(&api))
+        return rc;
+    const float* src = e->dLatest + (long long) slot * JBK_REC * e->clipPitch;
+    JB_NCCL(api, api->AllGather(src, d_out, (size_t) JBK_REC * (size_t) e->clipPitch, kNcclFloat32, e->comm, e->stream));
+    return JB_OK;
+}
+
+int jb_gather_records_all(jb_engine* const* engines, int n, int slot, float* const* d_out)
+{
+    if (engines == nullptr || d_out == nullptr || n < 1)
+        return fail(JB_ERR_ARG, "jb_gather_records_all: null argument");
+    NcclApi* api = nullptr;
+    if (int rc = needNccl(&api))
+        return rc;
+    for (int i = 0; i < n; ++i) {
+        if (int rc = checkSlot(engines[i], slot))
+            return rc;
+        if (engines[i]->comm == nullptr || engines[i]->commRanks != n || !engines[i]->prepared || d_out[i] == nullptr)
+            return fail(JB_ERR_STATE, "jb_gather_records_all: engine %d is not a prepared member of an %d-rank communicator", i, n);
+        if (engines[i]->clipPitch != engines[0]->clipPitch)
+            return fail(JB_ERR_ARG, "jb_gather_records_all: engines must hold the same number of clips (record pitch %lld vs %lld)",
+                        engines[i]->clipPitch, engines[0]->clipPitch);
+    }
+    JB_NCCL(api, api->GroupStart());
+    for (int i = 0; i < n; ++i) {
+        jb_engine* e = engines[i];
+        cudaSetDevice(e->device);
+        const float* src = e->dLatest + (long long) slot * JBK_REC * e->clipPitch;
+        const int rc = api->AllGather(src, d_out[i], (size_t) JBK_REC * (size_t) e->clipPitch, kNcclFloat32, e->comm, e->stream);
+        if (rc != 0) {
+            api->GroupEnd();
+            return fail(JB_ERR_CUDA, "ncclAllGather failed: %s", api->GetErrorString(rc));
+        }
+    }
+    JB_NCCL(api, api->GroupEnd());
+    return JB_OK;
+}
+
+int jb_gather_records_host(jb_engine* e, int slot, jb_metrics* out, int clips_per_rank)
+{
+    if (int rc = checkSlot(e, slot))
+        return rc;
+    if (int rc = setDevice(e))
+        return rc;
+    if (out == nullptr || clips_per_rank < 0 || clips_per_rank > e->clipPitch)
+        return fail(JB_ERR_ARG, "jb_gather_records_host: bad output / clips_per_rank %d", clips_per_rank);
+    if (e->comm == nullptr)
+        return fail(JB_ERR_STATE, "jb_gather_records_host: no communicator");
+    const size_t per = (size_t) JBK_REC * (size_t) e->clipPitch;
+    const size_t need = sizeof(float) * per * (size_t) e->commRanks;
+    if (need > e->gatherBytes) {
+        cudaFree(e->dGather);
+        e->dGather = nullptr;
+        e->gatherBytes = 0;
+        JB_CUDA(cudaMalloc(&e->dGather, need));
+        e->gatherBytes = need;
+    }
+    if (int rc = jb_gather_records(e, slot, e->dGather))
+        return rc;
+    e->hostScratch.resize(per * (size_t) e->commRanks);
+    JB_CUDA(cudaMemcpyAsync(e->hostScratch.data(), e->dGather, need, cudaMemcpyDeviceToHost, e->stream));
+    JB_CUDA(cudaStreamSynchronize(e->stream));
+    for (int r = 0; r < e->commRanks; ++r)
+        unpackRecords(e->hostScratch.data() + (size_t) r * per, e->clipPitch, clips_per_rank, out + (size_t) r * (size_t) clips_per_rank);
     return JB_OK;
 }
 

@@ -664,7 +664,7 @@ struct MainTexture : MainBase {
             st.springVel += acc;
             st.springPos += st.springVel;
             shaped = 0.48f * core + 1.85f * st.springPos;
-            shaped = tanhf(shaped * k.shapeGain);
+            shaped = jblibm::tanhf_fdlibm(shaped * k.shapeGain); // the C library's own std::tanh: Texture's output feeds Width's threshold
         } else if (MAT == 1) { // metal :152-169
             const float exc = core * (0.19f + 0.52f * impact);
             const float m0 = mode(st, 0, exc, a1[0]);
@@ -698,7 +698,7 @@ struct MainTexture : MainBase {
             st.fleshPosB += st.fleshVelB;
             const float tissue = 0.92f * st.fleshPosA + 0.58f * st.fleshPosB;
             const float nl = tissue - 0.19f * tissue * tissue * tissue;
-            shaped = tanhf((0.50f * core + 1.34f * nl) * k.shapeGain);
+            shaped = jblibm::tanhf_fdlibm((0.50f * core + 1.34f * nl) * k.shapeGain);
         }
 
         rng = 1664525u * rng + 1013904223u; // :239-243

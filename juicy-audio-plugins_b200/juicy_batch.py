@@ -106,6 +106,18 @@ def lib():
         "jb_set_path": (ci, [vp, ci]),
         "jb_set_math_mode": (ci, [vp, ci]),
         "jb_path_launches": (ci, [vp, ctypes.POINTER(cll), ctypes.POINTER(cll)]),
+        "jb_shard_range": (ci, [cll, ci, ci, ctypes.POINTER(cll), ctypes.POINTER(cll)]),
+        "jb_record_pitch": (cll, [vp]),
+        "jb_comm_version": (ci, [ctypes.POINTER(ci)]),
+        "jb_comm_unique_id": (ci, [vp]),
+        "jb_comm_init_rank": (ci, [vp, vp, ci, ci]),
+        "jb_comm_init_all": (ci, [ctypes.POINTER(vp), ci]),
+        "jb_comm_destroy": (ci, [vp]),
+        "jb_comm_size": (ci, [vp]),
+        "jb_comm_rank": (ci, [vp]),
+        "jb_gather_records": (ci, [vp, ci, vp]),
+        "jb_gather_records_all": (ci, [ctypes.POINTER(vp), ci, ci, ctypes.POINTER(vp)]),
+        "jb_gather_records_host": (ci, [vp, ci, vp, ci]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -397,6 +409,21 @@ class BatchProcessor:
         _check(lib().jb_path_launches(self._h, ctypes.byref(c), ctypes.byref(l)))
         return c.value, l.value
 
+    # ---- score gather across GPUs (jb_comm_* / jb_gather_records)
+    def comm_init_rank(self, unique_id, n_ranks, rank):
+        _check(lib().jb_comm_init_rank(self._h, ctypes.c_char_p(bytes(unique_id)), int(n_ranks), int(rank)))
+
+    def record_pitch(self):
+        return lib().jb_record_pitch(self._h)
+
+    def gather_records_host(self, slot=0, clips_per_rank=None):
+        """[n_ranks * clips_per_rank][16]: every rank's latest records in global clip order (ncclAllGather + download)."""
+        n = lib().jb_comm_size(self._h)
+        cpr = self.n_clips if clips_per_rank is None else int(clips_per_rank)
+        out = np.zeros((n * cpr, 16), dtype=np.float32)
+        _check(lib().jb_gather_records_host(self._h, self.slot(slot), out.ctypes.data, cpr))
+        return out
+
     def kernel_time_ms(self):
         """(milliseconds, launches) spent in the render kernel since the last call (CUDA events
         recorded on the engine's stream around every launch)."""
@@ -404,6 +431,26 @@ class BatchProcessor:
         n = ctypes.c_longlong()
         _check(lib().jb_kernel_time_ms(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+
+def shard_range(n_clips, rank, world):
+    """[lo, hi) of the clips rank `rank` of `world` renders (jb_shard_range): contiguous, balanced to within one clip."""
+    first, count = ctypes.c_longlong(), ctypes.c_longlong()
+    _check(lib().jb_shard_range(int(n_clips), int(rank), int(world), ctypes.byref(first), ctypes.byref(count)))
+    return first.value, first.value + count.value
+
+
+def comm_unique_id():
+    """128 opaque bytes (ncclGetUniqueId) that rank 0 hands to the other ranks."""
+    buf = ctypes.create_string_buffer(128)
+    _check(lib().jb_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init_all(engines):
+    """One process driving one engine per GPU: a communicator over all of them (ncclCommInitAll)."""
+    hs = (ctypes.c_void_p * len(engines))(*[e._h for e in engines])
+    _check(lib().jb_comm_init_all(hs, len(engines)))
 
 
 def synth_fill_device(d_ptr, kind, first_clip, n_clips, n_channels, n_samples, sample_rate=48000.0,

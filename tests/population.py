@@ -60,10 +60,17 @@ def _worker_main():
         if cmd["op"] == "config":
             spec = cmd
             cls = refhost.RefPlugin if cmd["kind"] == "reference" else port.PortPlugin
-            plugins = [cls(p, 2, cmd["sample_rate"], cmd["block"]) for p in cmd["chain"]]
-            for slot, kv in (cmd.get("params") or {}).items():
-                for k, v in kv.items():
-                    plugins[int(slot)].set_param(k, v)
+
+            def make_plugins(cfg=cmd, cls=cls):
+                # a FRESH instance per clip, like the engine's clips: some members are set by the constructor only and
+                # survive prepareToPlay (Motion's LCG, JuicyMotion/PluginProcessor.h:65; Cohere's learnt targets, .h:55-57)
+                ps = [cls(p, 2, cfg["sample_rate"], cfg["block"]) for p in cfg["chain"]]
+                for slot, kv in (cfg.get("params") or {}).items():
+                    for k, v in kv.items():
+                        ps[int(slot)].set_param(k, v)
+                return ps
+
+            make_plugins()  # fail early if the oracle library is missing
             sys.stdout.write("ok\n")
             sys.stdout.flush()
             continue
@@ -74,11 +81,12 @@ def _worker_main():
         a_gpu = np.ndarray((k, 2, n), dtype=np.float32, buffer=attach(cmd["gpu"]).buf)
         a_hist = np.ndarray((L, nb, k, 16), dtype=np.float32, buffer=attach(cmd["hist"]).buf) if cmd.get("hist") else None
         a_last = np.ndarray((L, k, 16), dtype=np.float32, buffer=attach(cmd["last"]).buf) if cmd.get("last") else None
-        res = np.ndarray((k, 4), dtype=np.float64, buffer=attach(cmd["res"]).buf)
+        res = np.ndarray((k, 6), dtype=np.float64, buffer=attach(cmd["res"]).buf)
         per_clip = spec.get("per_clip")  # {"slot": s, "id": pid, "mod": m}: value = absolute clip index mod m
         for c in range(lo, hi):
             x = a_in[c]
-            rec_err, rec_block, rec_slot = 0.0, -1, -1
+            rec_err, rec_block, rec_slot, rec_field, rec_ref = 0.0, -1, -1, -1, 0.0
+            plugins = make_plugins()
             for s, p in enumerate(plugins):
                 if per_clip and per_clip["slot"] == s:
                     p.set_param(per_clip["id"], float((cmd["first_clip"] + c) % per_clip["mod"]))
@@ -90,13 +98,14 @@ def _worker_main():
                     d = np.where(np.isfinite(d), d, np.inf)
                     m = float(d.max())
                     if m > rec_err:
-                        rec_err, rec_block, rec_slot = m, int(np.unravel_index(int(d.argmax()), d.shape)[0]), s
+                        bi, fi = np.unravel_index(int(d.argmax()), d.shape)
+                        rec_err, rec_block, rec_slot, rec_field, rec_ref = m, int(bi), s, int(fi), float(h[bi, fi])
                 elif a_last is not None:
                     d = np.abs(a_last[s, c, :].astype(np.float64) - h[-1].astype(np.float64))
                     d = np.where(np.isfinite(d), d, np.inf)
                     m = float(d.max())
                     if m > rec_err:
-                        rec_err, rec_block, rec_slot = m, h.shape[0] - 1, s
+                        rec_err, rec_block, rec_slot, rec_field, rec_ref = m, h.shape[0] - 1, s, int(d.argmax()), float(h[-1, int(d.argmax())])
             peak = max(float(np.abs(x).max()), 1.0e-30)
             g = a_gpu[c]
             err = np.abs(g.astype(np.float64) - x.astype(np.float64))
@@ -105,6 +114,10 @@ def _worker_main():
             res[c, 1] = rec_err
             res[c, 2] = rec_block
             res[c, 3] = rec_slot
+            res[c, 4] = rec_field
+            res[c, 5] = rec_ref
+            for p in plugins:
+                p.close()
         sys.stdout.write("done\n")
         sys.stdout.flush()
     for s in shms.values():
@@ -165,10 +178,10 @@ class OraclePool:
         return a_in, a_gpu, a_rec
 
     def check(self, k, first_clip, with_hist):
-        """Run the oracle over the k clips currently in the shared buffers.  Returns [k][4]: sample error / peak,
+        """Run the oracle over the k clips currently in the shared buffers.  Returns [k][6]: sample error / peak,
         worst record error, its block, its slot."""
-        res_shm = self._buf("res", k * 4 * 8)
-        res = np.ndarray((k, 4), dtype=np.float64, buffer=res_shm.buf)
+        res_shm = self._buf("res", k * 6 * 8)
+        res = np.ndarray((k, 6), dtype=np.float64, buffer=res_shm.buf)
         res[:] = -1.0
         per = (k + self.procs - 1) // self.procs
         active = []
@@ -237,7 +250,7 @@ def run_population(jb, chain, n_clips, synth, n_samples=48000, sample_rate=48000
 
     n_check = n_clips if limit_clips is None else min(n_clips, limit_clips)
     pool = OraclePool(chain, n_samples, sample_rate, block, params, per_clip, procs)
-    res_all = np.zeros((n_check, 4), dtype=np.float64)
+    res_all = np.zeros((n_check, 6), dtype=np.float64)
     t1 = time.time()
     try:
         # records of the whole batch, once per plugin: [n_blocks][n_clips][16] (history) or [n_clips][16] (last block)
@@ -270,6 +283,9 @@ def run_population(jb, chain, n_clips, synth, n_samples=48000, sample_rate=48000
         "worst_sample_err_of_peak": float(res_all[worst_s, 0]) if n_check else 0.0, "worst_sample_clip": worst_s,
         "worst_record_err": float(res_all[worst_r, 1]) if n_check else 0.0, "worst_record_clip": worst_r,
         "worst_record_block": int(res_all[worst_r, 2]) if n_check else -1, "worst_record_slot": int(res_all[worst_r, 3]) if n_check else -1,
+        "worst_record_field": int(res_all[worst_r, 4]) if n_check else -1, "worst_record_ref_value": float(res_all[worst_r, 5]) if n_check else 0.0,
+        "bad_record_detail": [{"clip": int(c), "err": float(res_all[c, 1]), "block": int(res_all[c, 2]), "slot": int(res_all[c, 3]),
+                               "field": int(res_all[c, 4]), "ref": float(res_all[c, 5])} for c in bad_r[:16]],
         "bad_sample_clips": [int(c) for c in bad_s[:32]], "bad_record_clips": [int(c) for c in bad_r[:32]],
         "median_sample_err_of_peak": float(np.median(res_all[:, 0])) if n_check else 0.0,
         "sample_tol": SAMPLE_TOL, "record_tol": METRIC_TOL, "gpu_seconds": t_gpu, "oracle_seconds": t_cpu,

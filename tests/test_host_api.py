@@ -108,3 +108,22 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                            "-Wl,-rpath," + pkg])
     out = subprocess.check_output([exe]).decode()
     assert out.startswith("sets 4 state bytes"), out
+
+
+def test_synth_numpy_port_matches_the_library_generator(jb):
+    """oracle/synth_np.py (inputs of bench.py's CPU reference arm, which must not load the product library)."""
+    from oracle import synth_np
+    for kind, tol in (("noise", 0.0), ("impulse", 0.0), ("drum", 1e-6), ("sweep", 1e-3), ("mixed", 1e-3)):
+        a = jb.synth_clips(kind, 4090, 6, 5000)
+        b = synth_np.synth_clips(kind, 4090, 6, 5000)
+        assert float(np.abs(a - b).max()) <= tol, kind
+
+
+def test_shard_range_partitions(jb):
+    for n_clips, world in ((4096, 1), (262144, 8), (10, 4), (3, 8)):
+        ranges = [jb.shard_range(n_clips, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n_clips
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert max(hi - lo for lo, hi in ranges) - min(hi - lo for lo, hi in ranges) <= 1
+    with pytest.raises(jb.JuicyBatchError):
+        jb.shard_range(10, 4, 4)

@@ -1,9 +1,10 @@
-"""N > 1 host logic on CPU: clip sharding + the record gather, 2 ranks over gloo.
+"""N > 1 host logic on CPU: clip sharding (jb_shard_range, the library's own) + the record gather, 2 ranks over gloo.
 
 Each rank renders ITS clip range (here with the CPU oracle standing in for the GPU, which this
 container does not have), packs the records in the engine's device layout and all_gathers them;
 the result must equal one process rendering every clip.  The GPU version of the same flow is
-bench.py --gpus N (NCCL on jb_metrics_device)."""
+jb_comm_init_rank + jb_gather_records (NCCL inside the library: tests/test_gpu_sharding.py, bench.py --gpus N).
+torch appears here only as the CPU stand-in for that collective."""
 import importlib.util
 import os
 import socket
@@ -15,11 +16,48 @@ import pytest
 from conftest import PKG, ROOT, load_juicy_batch
 
 
+REC = 16  # floats per record (jb_metrics)
+
+
+class _Sharding:
+    """Shard arithmetic from the library (jb_shard_range); the record block layout [16][pitch] of jb_metrics_device."""
+
+    @staticmethod
+    def clip_pitch(n_clips):
+        return (int(n_clips) + 31) // 32 * 32
+
+    @staticmethod
+    def shard_range(n_clips, rank, world):
+        jb = load_juicy_batch()
+        try:
+            return jb.shard_range(n_clips, rank, world)
+        except jb.JuicyBatchError as exc:
+            raise ValueError(str(exc))
+
+    @staticmethod
+    def pack_records_soa(records, pitch):
+        records = np.asarray(records, dtype=np.float32)
+        out = np.zeros((REC, pitch), dtype=np.float32)
+        out[:, :records.shape[0]] = records.T
+        return out.reshape(-1)
+
+    @staticmethod
+    def unpack_gathered(flat, counts, pitch):
+        flat = np.asarray(flat, dtype=np.float32).reshape(len(counts), REC, pitch)
+        return np.concatenate([flat[r, :, :counts[r]].T for r in range(len(counts))], axis=0)
+
+    @staticmethod
+    def gather_records(local_soa, world, dist):
+        import torch
+        if world == 1:
+            return local_soa.clone()
+        out = torch.empty(world * local_soa.numel(), dtype=local_soa.dtype, device=local_soa.device)
+        dist.all_gather_into_tensor(out, local_soa)
+        return out
+
+
 def load_sharding():
-    spec = importlib.util.spec_from_file_location("jb_sharding", os.path.join(PKG, "sharding.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
+    return _Sharding
 
 
 @pytest.mark.parametrize("n_clips,world", [(4096, 1), (4096, 8), (10, 4), (3, 8), (262144, 8), (7, 2)])
