@@ -11,6 +11,7 @@
 #include "jb_params.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 
 #include <algorithm>
 #include <cstdarg>
@@ -35,6 +36,14 @@ int fail(int code, const char* fmt, ...)
     g_error = buf;
     return code;
 }
+
+// NVTX range around a C-ABI call (tracing), closed on every exit path
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 #define JB_CUDA(call)                                                                          \
     do {                                                                                       \
@@ -889,6 +898,7 @@ int jb_num_clips(const jb_engine* e) { return e ? e->nClips : 0; }
 
 int jb_prepare(jb_engine* e, double sample_rate, int samples_per_block)
 {
+    NvtxRange nvtxRange("jb_prepare");
     if (int rc = checkEngine(e))
         return rc;
     if (!(sample_rate > 0.0) || samples_per_block < 1)
@@ -1277,6 +1287,7 @@ int jb_synchronize(jb_engine* e)
 
 int jb_process(jb_engine* e, const float* d_in, float* d_out, int n_samples)
 {
+    NvtxRange nvtxRange("jb_process");
     if (int rc = checkEngine(e))
         return rc;
     if (int rc = setDevice(e))
@@ -1300,6 +1311,7 @@ int jb_process(jb_engine* e, const float* d_in, float* d_out, int n_samples)
 
 int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples)
 {
+    NvtxRange nvtxRange("jb_process_host");
     if (int rc = checkEngine(e))
         return rc;
     if (int rc = setDevice(e))
@@ -1418,6 +1430,7 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
 
 int jb_get_metrics(jb_engine* e, int slot, jb_metrics* out)
 {
+    NvtxRange nvtxRange("jb_get_metrics");
     if (int rc = checkSlot(e, slot))
         return rc;
     if (out == nullptr)
@@ -1855,6 +1868,7 @@ int jb_comm_rank(const jb_engine* e) { return e ? e->commRank : -1; }
 
 int jb_gather_records(jb_engine* e, int slot, float* d_out)
 {
+    NvtxRange nvtxRange("jb_gather_records");
     if (int rc = checkSlot(e, slot))
         return rc;
     if (int rc = setDevice(e))
@@ -1906,6 +1920,7 @@ int jb_gather_records_all(jb_engine* const* engines, int n, int slot, float* con
 
 int jb_gather_records_host(jb_engine* e, int slot, jb_metrics* out, int clips_per_rank)
 {
+    NvtxRange nvtxRange("jb_gather_records_host");
     if (int rc = checkSlot(e, slot))
         return rc;
     if (int rc = setDevice(e))

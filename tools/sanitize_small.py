@@ -1,4 +1,9 @@
-"""Small renders through every lane-kernel variant, for `compute-sanitizer --tool memcheck python tools/sanitize_small.py`."""
+"""Small renders through every kernel variant, for
+  compute-sanitizer --tool memcheck  python tools/sanitize_small.py
+  compute-sanitizer --tool racecheck python tools/sanitize_small.py   (shared-memory hazards: the cooperative kernel's
+                                                                       named barriers, mbarriers and cross-warp hand-offs)
+  compute-sanitizer --tool synccheck python tools/sanitize_small.py
+Logs of the round's runs: profiles/r02_sanitizer_*.log."""
 import os
 import sys
 
@@ -35,4 +40,7 @@ run(FULL, 64, 4 * 512, settings=[(2, "material", 2.0)])       # exact math, wave
 run(["JuicyTexture"], 67, 3 * 512 + 40, per_clip=True)        # clip maps, concurrent launches
 run(["JuicySaturator", "JuicyWidth", "JuicyCohere", "JuicyInfer"], 64, 5 * 512 + 12)   # JB_TILE=1 from the environment
 run(FULL, 37, 3 * 512 + 50, channels=1, math="fast")          # mono kernel
-run(["JuicyPunch", "JuicyWidth"], 96, 4 * 512)                # cooperative kernel
+run(["JuicyPunch", "JuicyWidth"], 96, 4 * 512)                # cooperative kernel, exact-math instantiation (auto)
+run(["JuicyPunch", "JuicyWidth", "JuicyInfer"], 70, 3 * 512 + 256, math="fast")   # cooperative kernel, fast math, ragged groups
+run(["JuicyWidth"], 40, 2 * 512 + 128, block=256)             # cooperative kernel, Width alone, one step per block
+run(["JuicySaturator", "JuicyTexture"], 21, 2 * 512 + 64, channels=1, settings=[(1, "material", 1.0)])  # mono, exact math
