@@ -71,6 +71,7 @@ struct CoopSmem {
     int widthPos[CO_GMAX];                      //   ring write position of the step's first sample
     int widthCount[CO_GMAX];                    //   multiplies so far in the current host block
     unsigned long long bar[2];                  //   mbarriers: tile slot filled
+    int claim[2];                               //   next unclaimed clip of the step in tile slot 0 / 1 (bulk work queue)
 };
 
 // ---------------------------------------------------------------- PTX wrappers (async proxy)
@@ -627,7 +628,7 @@ struct CoopArgs {
     int debugSkip;      // profiling builds (-DJB_COOP_DEBUG, JB_COOP_DEBUG_SKIP): bit 0 envelope walk, 1 band walk, 2 bulk math, 3 scout
 };
 
-template <bool EXACT>
+template <bool EXACT, bool ISOLATE>
 __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_constant__ CoopArgs ca)
 {
     extern __shared__ __align__(1024) unsigned char smemRaw[];
@@ -648,17 +649,12 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
     // A warp's scheduler (SM sub-partition) is warp % 4.  The envelope warps carry the kernel's critical
     // sequential chain and every one of their instructions is on it, so they get sub-partition 3 to
     // themselves (its other warps idle); everybody else shares sub-partitions 0..2.
-#if JB_CO_ISOLATE
-    const bool onSeqPartition = (warp & 3) == 3;
-    const int seqIdx = warp >> 2;                 // index among the warps of sub-partition 3
-    const int parIdx = warp - ((warp + 1) >> 2);  // index among the others
-    const int nPar = CO_WARPS - CO_WARPS / 4;
-#else
-    const bool onSeqPartition = warp >= CO_WARPS - nAna;
-    const int seqIdx = warp - (CO_WARPS - nAna);
-    const int parIdx = warp;
-    const int nPar = CO_WARPS - nAna;
-#endif
+    // ISOLATE = false (exact math: the bulk warps' pow / tanh dominate and want all four schedulers): roles by plain warp
+    // index, envelope warps highest.
+    const bool onSeqPartition = ISOLATE ? (warp & 3) == 3 : warp >= CO_WARPS - nAna;
+    const int seqIdx = ISOLATE ? warp >> 2 : warp - (CO_WARPS - nAna);  // index among the warps of sub-partition 3
+    const int parIdx = ISOLATE ? warp - ((warp + 1) >> 2) : warp;       // index among the others
+    const int nPar = ISOLATE ? CO_WARPS - CO_WARPS / 4 : CO_WARPS - nAna;
     const int wScout = 1, wBand = wScout + CO_NSCOUT, wBulk = wBand + nAna;
     const int nBulk = nPar - wBulk;
     const bool isProducerWarp = !onSeqPartition && parIdx == 0;
@@ -733,6 +729,8 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             sm.widthPos[threadIdx.x] = __float_as_int(a.state[(long long) (b + WV_WPOS) * a.clipPitch + clip0 + threadIdx.x]);
             sm.widthCount[threadIdx.x] = 0;
         }
+        if (threadIdx.x == 0)
+            sm.claim[gstep & 1] = 0;
 
         Cursor cur = cursor_at(a, 0, 0);
         auto issue_load = [&](const Cursor& c, unsigned step) {
@@ -829,30 +827,48 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             const int blockPar = cur.blk & 1;
 
             if (isProducerWarp) {
+                if (lane == 0)
+                    sm.claim[slot ^ 1] = 0; // the next step's work queue (nobody reads it before the barrier below)
                 if (nxt.valid) {
                     bulk_wait_read(); // the store that last read the other slot has drained
                     issue_load(nxt, step + 1);
                 }
-            } else if (isScoutWarp) {
-                if (nxt.valid)
-                    scout_step(nxt, step + 1);
-            } else if (isEnvWarp || isBandWarp) {
-                // analyzers run one host block behind: pre-analysis of block blk-1 during the first
-                // step of block blk, post-analysis during the second (or both, if blk is one step long)
-                if (cur.blk > 0) {
-                    const bool single = cur.nBlk <= CO_T;
-                    if (cur.off == 0)
-                        analyze_pre(cur.blk - 1, a.blockSize);
-                    if (single || cur.off == CO_T)
-                        analyze_post(cur.blk - 1, a.blockSize);
+            } else {
+                if (isScoutWarp) {
+                    if (nxt.valid)
+                        scout_step(nxt, step + 1);
+                } else if (isEnvWarp || isBandWarp) {
+                    // analyzers run one host block behind: pre-analysis of block blk-1 during the first
+                    // step of block blk, post-analysis during the second (or both, if blk is one step long)
+                    if (cur.blk > 0) {
+                        const bool single = cur.nBlk <= CO_T;
+                        if (cur.off == 0)
+                            analyze_pre(cur.blk - 1, a.blockSize);
+                        if (single || cur.off == CO_T)
+                            analyze_post(cur.blk - 1, a.blockSize);
+                    }
                 }
-            } else if (isBulkWarp) {
-                // ---- bulk warps
+                // ---- bulk work: the step's clips are a queue in shared memory, claimed one at a time.  The bulk warps
+                // live on it; scout and band warps join once their own (short) work of the step is done.  With the exact
+                // routines the bulk math is the larger part (116 / 93 issue cycles per tanhf / powf against 20 / 16 for the
+                // MUFU forms, profiles/microbench/exact_math.cu), so there the envelope warps and the otherwise idle warps of
+                // their scheduler take clips too; with fast math the envelope walk is the critical chain and its warps keep
+                // to it.  (Measured: the queue balances the step but the exact kernel stays dependency-bound -- 0.84 eligible
+                // warps per scheduler at 16 warps per SM, profiles/r02_coop_exact_ncu.json; 20 / 24 / 32 warps with fewer
+                // registers gave 7.0 / 6.9 / 7.6 ms against 7.3, and cost the fast instantiation 0.4 - 1.1 ms.)
+                const bool joins = isBulkWarp || isScoutWarp || isBandWarp || EXACT;
+                if (joins) {
                 mbar_wait(&sm.bar[slot], (step >> 1) & 1);
                 const int nValid = max(0, min(CO_CH, cur.n - lane * CO_CH));
                 const bool firstStep = cur.off == 0;
                 const bool ragged = cur.n < CO_T; // warp-uniform
-                for (int ci = parIdx - wBulk; ci < G && !(dbgSkip & 4); ci += nBulk) {
+                while (!(dbgSkip & 4)) {
+                    int ci = 0;
+                    if (lane == 0)
+                        ci = atomicAdd(&sm.claim[slot], 1);
+                    ci = __shfl_sync(0xffffffffu, ci, 0);
+                    if (ci >= G)
+                        break;
                     float* rowL = &sm.tile[slot][2 * ci][lane * CO_CH];
                     float* rowR = &sm.tile[slot][2 * ci + 1][lane * CO_CH];
                     float l[CO_CH], r[CO_CH];
@@ -875,8 +891,10 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                         const SlotDesc& d = a.slot[s];
                         if (d.kind == K_PUNCH) {
                             const float2 zero = make_float2(0.0f, 0.0f); // lanes past the step's end have no checkpoint
-                            punch_chunk<EXACT>(l, nValid > 0 ? sm.ckpt[slot][2 * ci][lane] : zero, d.c.punch);
-                            punch_chunk<EXACT>(r, nValid > 0 ? sm.ckpt[slot][2 * ci + 1][lane] : zero, d.c.punch);
+                            const float2 ckL = nValid > 0 ? sm.ckpt[slot][2 * ci][lane] : zero;
+                            const float2 ckR = nValid > 0 ? sm.ckpt[slot][2 * ci + 1][lane] : zero;
+                            punch_chunk<EXACT>(l, ckL, d.c.punch);
+                            punch_chunk<EXACT>(r, ckR, d.c.punch);
                         } else if (d.kind == K_WIDTH) {
                             int total = 0;
                             const int kStart = firstStep ? 0 : sm.widthCount[ci];
@@ -904,6 +922,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                     *reinterpret_cast<float4*>(rowR + 4) = make_float4(r[4], r[5], r[6], r[7]);
                 }
                 fence_async_smem(); // tile writes -> visible to the bulk store issued after the barrier
+                }
             }
             __syncthreads();
             if (isProducerWarp) {
@@ -997,9 +1016,15 @@ int jbk_launch_coop(const ProcArgs* args, float* monoScratch, int numSMs, void* 
 {
     if (args->nClips <= 0 || args->nSamples <= 0)
         return 0;
-    for (int v = 0; v < 2; ++v) {
-        cudaError_t e = v ? cudaFuncSetAttribute(jb_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CoopSmem))
-                          : cudaFuncSetAttribute(jb_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CoopSmem));
+    // Envelope warps alone on one scheduler pays while their sequential walk is the kernel's critical path (fast math);
+    // with the exact routines the bulk warps are, and they get all four (profiles/r02_coop_variants.txt).  JB_CO_ISOLATE=0/1 forces.
+    static const int isoEnv = [] { const char* v = getenv("JB_CO_ISOLATE"); return v == nullptr ? -1 : atoi(v); }();
+    const bool exact = args->exactMath != 0;
+    const bool isolate = isoEnv < 0 ? !exact : isoEnv != 0;
+    void (*kernel)(const CoopArgs) = exact ? (isolate ? jb_coop_kernel<true, true> : jb_coop_kernel<true, false>)
+                                           : (isolate ? jb_coop_kernel<false, true> : jb_coop_kernel<false, false>);
+    {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(CoopSmem));
         if (e != cudaSuccess) {
             snprintf(g_coopErr, sizeof g_coopErr, "cudaFuncSetAttribute(jb_coop_kernel): %s", cudaGetErrorString(e));
             return -1;
@@ -1020,10 +1045,41 @@ int jbk_launch_coop(const ProcArgs* args, float* monoScratch, int numSMs, void* 
     ca.debugSkip = 0;
 #endif
     const int grid = ca.numGroups < numSMs ? ca.numGroups : numSMs;
-    if (args->exactMath)
-        jb_coop_kernel<true><<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
-    else
-        jb_coop_kernel<false><<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
+    // The analyzer lanes re-read the mono scratch one host block after the bulk warps wrote it; it is a ring that is
+    // overwritten all the time, so none of it ever has to reach HBM -- but with the per-access evict_last hint alone ~60 %
+    // of its lines were still written back (ncu: dram__bytes_write 2.9 GB against 1.6 GB of audio, profiles/
+    // r02_coop_exact_ncu.json).  A persisting-L2 access window over the ring for the duration of the launch keeps it
+    // resident; the window is taken down again right behind the kernel.  JB_COOP_L2_WINDOW=0 disables.
+    static const bool useWindow = [] { const char* v = getenv("JB_COOP_L2_WINDOW"); return v == nullptr || atoi(v) != 0; }();
+    bool windowSet = false;
+    if (useWindow) {
+        static thread_local int limitDev = -1;
+        int dev = 0, maxWindow = 0, maxPersist = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        const size_t ringBytes = sizeof(float) * (size_t) grid * CO_GMAX * (size_t) (args->chainLen + 1) * 2 * CO_BLOCKMAX;
+        if (maxWindow > 0 && maxPersist > 0) {
+            if (limitDev != dev) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t) maxPersist);
+                limitDev = dev;
+            }
+            cudaStreamAttrValue attr = {};
+            attr.accessPolicyWindow.base_ptr = monoScratch;
+            attr.accessPolicyWindow.num_bytes = ringBytes < (size_t) maxWindow ? ringBytes : (size_t) maxWindow;
+            attr.accessPolicyWindow.hitRatio = ringBytes <= (size_t) maxPersist ? 1.0f : (float) ((double) maxPersist / (double) ringBytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            windowSet = cudaStreamSetAttribute((cudaStream_t) stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+            cudaGetLastError();
+        }
+    }
+    kernel<<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
+    if (windowSet) {
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute((cudaStream_t) stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    }
     jbk_note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
