@@ -368,7 +368,7 @@ int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params
     a.recChainLen = a.chainLen;
     const bool aligned = ((reinterpret_cast<uintptr_t>(dIn) | reinterpret_cast<uintptr_t>(dOut)) & 15u) == 0;
     a.vecOk = (aligned && nSamples % 4 == 0 && a.rowPitch % 4 == 0 && e->blockSize % 4 == 0) ? 1 : 0;
-    a.lightOctets = 0; // per launch, see octetsFor()
+    a.laneOnly = e->pathMode == 1 ? 1 : 0;
     a.octets = 0; // single-plugin engines: set below, once the math mode of this launch is known
     if (e->chain.size() > 1) { // fused generic kernel: eight samples per trip only when every plugin is light
         a.octets = nClips >= 32768 ? 1 : 0;
@@ -476,6 +476,8 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
     bool coop = allowCoop && a.nCh == 2 && e->coopCapable && e->dCoopScratch != nullptr && jbk_coop_supported(&a) != 0;
     if (e->pathMode == 1)
         coop = false;
+    else if (e->pathMode == 0 && coop && jbk_solo_pick(&a))
+        coop = false; // a few clips of one plugin: the clip-per-CTA kernel is ahead of the cooperative one (profiles/r02_solo.txt)
     else if (e->pathMode == 2 && !coop)
         return fail(JB_ERR_UNSUPPORTED, "cooperative path forced but this chain / call shape is not supported by it");
     else if (e->pathMode == 0 && coop) {
@@ -747,7 +749,6 @@ int renderClips(jb_engine* e, const float* dIn, float* dOut, int ns, int nc, lon
             buildArgs(e, a, paramsOfSet(e, g.set), dIn - c0 * clipStride, dOut - c0 * clipStride, ns, (int) (i1 - i0), 0, rowPitch);
             a.clipMap = e->dClipMap + g.mapOffset + (i0 - m);
             a.octets = 0;
-            a.lightOctets = 0;
         }
         cudaStream_t st = e->stream;
         if (!serial) {

@@ -97,6 +97,9 @@ int envInt(const char* name, int dflt) { const char* v = getenv(name); return v 
 // 32768 where the one-lane kernel switches to eight samples per trip; with the exact routines faster at every size
 const int g_pairLimitTexture = envInt("JB_PAIR_LIMIT_TEXTURE", 24576), g_pairLimitExact = envInt("JB_PAIR_LIMIT_EXACT", 1 << 30),
           g_pairLimitFast = envInt("JB_PAIR_LIMIT_FAST", 24576);
+// clip-per-CTA kernel up to this many clips (measured, profiles/r02_solo.txt: Saturator 592 clips 2.2 ms against 4.2 ms on two
+// lanes per clip, 1184 clips 4.4 against 4.2; JuicyInfer against the cooperative kernel alike): six CTAs per SM
+const int g_soloLimit = envInt("JB_SOLO_LIMIT", 888);
 const bool g_forceGeneric = [] { const char* v = getenv("JB_LANE_GENERIC"); return v != nullptr && atoi(v) != 0; }();
 
 int check(cudaError_t e, const char* what)
@@ -112,6 +115,8 @@ int check(cudaError_t e, const char* what)
 extern "C" int jbk_launch_single(const ProcArgs* args, int grid, void* stream); // jb_single_light.cu
 extern "C" int jbk_launch_mono(const ProcArgs* args, int grid, void* stream);        // jb_mono.cu
 extern "C" int jbk_pair_supported(const ProcArgs* args);                          // jb_pair.cu
+extern "C" int jbk_solo_supported(const ProcArgs* args);                          // jb_solo.cu
+extern "C" int jbk_launch_solo(const ProcArgs* args, void* stream);
 extern "C" int jbk_launch_pair(const ProcArgs* args, void* stream);
 
 extern "C" {
@@ -119,6 +124,13 @@ extern "C" {
 const char* jbk_last_cuda_error(void) { return g_cudaErr; }
 long long jbk_launch_count(void) { return g_launches; }
 void jbk_note_launch(void) { ++g_launches; }
+
+// Would jbk_launch_process render this single-plugin launch with the clip-per-CTA kernel?
+int jbk_solo_pick(const ProcArgs* args)
+{
+    return args->chainLen == 1 && g_soloLimit > 0 && !args->laneOnly && args->nClips <= g_soloLimit && jbk_solo_supported(args) != 0
+           && (!g_forceGeneric || args->exactMath);
+}
 
 int jbk_launch_process(const ProcArgs* args, void* stream)
 {
@@ -132,6 +144,10 @@ int jbk_launch_process(const ProcArgs* args, void* stream)
     if (args->chainLen > 1 && args->exactMath)
         return check(cudaErrorInvalidValue, "exact math needs one launch per plugin (the fused kernel has the fast routines only)");
     if (args->chainLen == 1 && (!g_forceGeneric || args->exactMath)) {
+        // Few live streams: one CTA per clip, everything but the analyzer's envelope walk taken off the sequential chain
+        // (jb_solo.cu).  Up to g_soloLimit clips (measured crossover against the lane kernels: profiles/r02_solo.txt).
+        if (jbk_solo_pick(args))
+            return check((cudaError_t) jbk_launch_solo(args, stream), "jb_solo_kernel launch");
         // Two lanes per clip (jb_pair.cu) while the batch is too small to keep the schedulers busy with one: measured
         // crossovers in profiles/r01_s6_pair.txt.  JB_PAIR=0 / 1 forces a choice.
         if (jbk_pair_supported(args)) {

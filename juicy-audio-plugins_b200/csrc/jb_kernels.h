@@ -157,7 +157,7 @@ struct ProcArgs {
                                   // of a record block laid out for recChainLen plugins
     int exactMath;         // Saturator / Punch: glibc-exact tanh / pow (jb_libm.h) instead of the MUFU-based ones
     int vecOk;             // 16-byte vector path legal (alignment + sizes)
-    int lightOctets;       // the `octets` mode a light plugin's launch of this call uses (chains rendered plugin by plugin)
+    int laneOnly;          // jb_set_path(JB_PATH_LANE): single-plugin launches take the lane kernels, not the clip-per-CTA one
     int octets;            // lane kernel: 8 samples per trip + 32-byte stores (set for big batches of light chains, where
                            // L2 sector throughput is the bound; costs registers, so not for Punch / Texture / Motion chains)
     AnaCoef ana;
@@ -169,6 +169,7 @@ extern "C" {
 #endif
 // jb_kernels.cu
 int jbk_launch_process(const ProcArgs* args, void* stream);
+int jbk_solo_pick(const ProcArgs* args); // few clips of one plugin: the clip-per-CTA kernel (jb_solo.cu) would take this launch
 int jbk_launch_fill(float* dst, float value, long long count, void* stream);
 int jbk_launch_synth(float* dAudio, int kind, long long firstClip, int nClips, int nCh, int nSamples,
                      double sampleRate, unsigned int seed, void* stream);
