@@ -412,6 +412,39 @@ class Bench:
             h_out.free()
         return secs, rec, in_place
 
+    def e2e_pcm16(self, steps, barrier):
+        """The same through jb_process_host_pcm16: 16-bit PCM host buffers (what audio files hold), converted on the device;
+        half the bytes per direction.  In place on the host side."""
+        jb, torch = self.jb, self.torch
+        n_clips, n = self.w["clips"], self.w["samples"]
+        h = jb.PinnedBuffer((n_clips, n))          # float32 words = 2 x int16: [n_clips][2 ch][n] int16
+        pcm = h.array.view(np.int16).reshape(n_clips, 2, n)
+        tmp = np.empty((min(n_clips, 512), 2, n), dtype=np.float32)
+
+        def fill():
+            for c0 in range(0, n_clips, tmp.shape[0]):
+                k = min(tmp.shape[0], n_clips - c0)
+                jb._check(jb.lib().jb_copy_to_host(self.local, tmp.ctypes.data, self.d_in.data_ptr() + c0 * 2 * n * 4, k * 2 * n * 4))
+                np.clip(np.rint(tmp[:k] * 32768.0), -32767, 32767, out=tmp[:k])
+                pcm[c0:c0 + k] = tmp[:k]
+
+        fill()
+        self.eng.reset()
+        self.eng.process_host_pcm16_ptr(pcm.ctypes.data, pcm.ctypes.data, n)
+        fill()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.eng.reset()
+            self.eng.process_host_pcm16_ptr(pcm.ctypes.data, pcm.ctypes.data, n)
+            self.eng.getLatestMetrics(self.last_slot)
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        barrier()
+        h.free()
+        return secs
+
     def close(self):
         try:
             self.eng.close()
@@ -422,7 +455,7 @@ class Bench:
 
 
 def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup, e2e_steps, comm_id, peak, peak_src,
-            with_fast=False):
+            with_fast=False, with_pcm=False):
     """Device-resident + end-to-end measurement of one workload; returns the result dict on rank 0 (None elsewhere)."""
     def barrier():
         if world > 1:
@@ -434,6 +467,7 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         sampler.start()
     ms_total, kernel_ms, kernel_renders, launches, coop, lane = b.timed(steps, warmup, barrier)
     e2e_s, rec_host, e2e_in_place = b.e2e(e2e_steps, barrier)
+    pcm_s = b.e2e_pcm16(e2e_steps, barrier) if with_pcm else 0.0
     clocks = sampler.stop() if rank == 0 else None
     fast = None
     if with_fast and world == 1:
@@ -441,10 +475,10 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         f_total, f_kernel, f_renders, _, _, _ = b.timed(max(2, steps // 2), 1, barrier)
         b.eng.set_math_mode("auto")
         fast = {"ms_per_step": f_total / max(2, steps // 2), "mean_render_ms": f_kernel / max(f_renders, 1)}
-    times = torch.tensor([ms_total, e2e_s * 1000.0, kernel_ms], dtype=torch.float64, device="cuda")
+    times = torch.tensor([ms_total, e2e_s * 1000.0, kernel_ms, pcm_s * 1000.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, kernel_ms = [float(x) for x in times.tolist()]
+    ms_total, e2e_ms, kernel_ms, pcm_ms = [float(x) for x in times.tolist()]
     b.close()
     if rank != 0:
         return None
@@ -484,6 +518,10 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         "math": "auto (exact tanh / pow where a Punch / Saturator feeds another plugin)",
         "mean_juiciness": float(np.mean(rec_host[:, 13])) if rec_host is not None else None,
     }
+    if with_pcm:
+        res["e2e_pcm16"] = {"value": world * ch_samples_rank * e2e_steps / (pcm_ms / 1000.0), "unit": UNIT, "ms_per_step": pcm_ms / e2e_steps,
+                            "h2d_bytes_per_step": count_bytes // 2, "d2h_bytes_per_step": count_bytes // 2 + 64 * w["clips"],
+                            "api": "jb_process_host_pcm16 + jb_get_metrics (pinned 16-bit PCM host buffers, device-side conversion)"}
     if fast:
         res["fast_math"] = {"ms_per_step": fast["ms_per_step"], "value": ch_samples_rank / (fast["ms_per_step"] / 1000.0),
                             "mean_render_ms": fast["mean_render_ms"],
@@ -529,13 +567,13 @@ def run_engine_arm(args):
     peak, peak_src = measured_peak_gbs()
     e2e_steps = max(1, min(args.steps, 5 if w["clips"] * w["samples"] > 1e9 else args.steps))
     res = measure(jb, torch, dist, w, name, local, rank, world, stream, args.steps, args.warmup, e2e_steps, comm_id, peak, peak_src,
-                  with_fast=True)
+                  with_fast=True, with_pcm=True)
 
     if rank == 0:
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(w, name)}
-        for k in ("roofline", "e2e", "gpu_launches", "clocks", "math", "mean_juiciness", "fast_math"):
+        for k in ("roofline", "e2e", "e2e_pcm16", "gpu_launches", "clocks", "math", "mean_juiciness", "fast_math"):
             if k in res:
                 line[k] = res[k]
         if world == 1 and not args.no_cpu:

@@ -159,6 +159,12 @@ int jb_process(jb_engine* e, const float* d_in, float* d_out, int n_samples);
  * pipelined fashion (copies overlapped with kernels); returns when h_out is
  * complete.  h_out may equal h_in. */
 int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples);
+/* The same with 16-bit PCM host buffers, planar [clip][channel][sample] (either side of the render is
+ * host<->device streaming, and 16-bit sources need not cross PCIe as 32-bit floats).  The device converts with the rule
+ * of jb_wav_read / jb_wav_write -- s / 32768 on the way in, round-half-even(v * 32768) limited to +-32767 on the way out --
+ * i.e. what the host's file reader / writer does around processBlock; the render in between is the fp32 one, bit for
+ * bit.  Half the bytes per direction of jb_process_host. */
+int jb_process_host_pcm16(jb_engine* e, const int16_t* h_in, int16_t* h_out, int n_samples);
 int jb_synchronize(jb_engine* e);
 /* Run on a caller-owned cudaStream_t (e.g. the framework's current stream). */
 int jb_set_stream(jb_engine* e, void* cuda_stream);

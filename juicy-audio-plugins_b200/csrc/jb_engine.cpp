@@ -117,6 +117,8 @@ struct jb_engine {
     // jb_process_host staging
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
     float* dStage[3] = { nullptr, nullptr, nullptr };
+    int16_t* dPcm[3] = { nullptr, nullptr, nullptr }; // 16-bit images of the staging buffers (jb_process_host_pcm16)
+    size_t pcmBytes[3] = { 0, 0, 0 };
     std::vector<cudaEvent_t> sliceEvents;
     cudaEvent_t evIn[3] = {}, evDone[3] = {}, evOut[3] = {};
     size_t stageBytes[3] = { 0, 0, 0 }; // capacity of each staging buffer (they grow independently)
@@ -214,6 +216,9 @@ void freeDevice(jb_engine* e)
     for (int i = 0; i < 3; ++i) {
         cudaFree(e->dStage[i]);
         e->dStage[i] = nullptr;
+        cudaFree(e->dPcm[i]);
+        e->dPcm[i] = nullptr;
+        e->pcmBytes[i] = 0;
         if (e->evIn[i]) cudaEventDestroy(e->evIn[i]);
         if (e->evDone[i]) cudaEventDestroy(e->evDone[i]);
         if (e->evOut[i]) cudaEventDestroy(e->evOut[i]);
@@ -1310,9 +1315,19 @@ int jb_process(jb_engine* e, const float* d_in, float* d_out, int n_samples)
     return JB_OK;
 }
 
-int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples)
+} // extern "C"
+
+extern "C" int jbk_launch_pcm16_to_float(const int16_t* src, float* dst, long long rows, int n, long long srcPitch, long long dstPitch, void* stream);
+extern "C" int jbk_launch_float_to_pcm16(const float* src, int16_t* dst, long long rows, int n, long long srcPitch, long long dstPitch, void* stream);
+
+namespace {
+
+// jb_process_host / jb_process_host_pcm16: host audio [clip][channel][sample] as fp32 or as 16-bit PCM (`pcm16`).
+int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, bool pcm16)
 {
-    NvtxRange nvtxRange("jb_process_host");
+    NvtxRange nvtxRange(pcm16 ? "jb_process_host_pcm16" : "jb_process_host");
+    const float* h_in = static_cast<const float*>(h_in_v);
+    float* h_out = static_cast<float*>(h_out_v);
     if (int rc = checkEngine(e))
         return rc;
     if (int rc = setDevice(e))
@@ -1364,6 +1379,17 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
             e->stageBytes[i] = need;
         }
     }
+    if (pcm16) { // 16-bit images of the staging buffers: what actually crosses PCIe
+        for (int i = 0; i < nBuffers; ++i) {
+            if (e->dPcm[i] == nullptr || need / 2 > e->pcmBytes[i]) {
+                cudaFree(e->dPcm[i]);
+                e->dPcm[i] = nullptr;
+                e->pcmBytes[i] = 0;
+                JB_CUDA(cudaMalloc(&e->dPcm[i], need / 2));
+                e->pcmBytes[i] = need / 2;
+            }
+        }
+    }
     while (e->sliceEvents.size() < (size_t) 2 * (size_t) nSlices) {
         cudaEvent_t ev = nullptr;
         JB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1396,6 +1422,7 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
         const long long c0 = (long long) pass * passClips;
         const int nc = (int) std::min<long long>(passClips, e->nClips - c0);
         float* dBuf = e->dStage[pass % nBuffers];
+        int16_t* dPcm = pcm16 ? e->dPcm[pass % nBuffers] : nullptr;
         const size_t rows = (size_t) nc * (size_t) e->nCh;
         const float* hIn = h_in + (size_t) c0 * e->nCh * n_samples;
         float* hOut = h_out + (size_t) c0 * e->nCh * n_samples;
@@ -1406,16 +1433,32 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
             const int t0 = firstBlock * e->blockSize;
             const int ns = std::min(n_samples - t0, sliceBlocks * e->blockSize);
             cudaEvent_t evIn = e->sliceEvents[(size_t) 2 * sl], evDone = e->sliceEvents[(size_t) 2 * sl + 1];
-            JB_CUDA(cudaMemcpy2DAsync(dBuf + t0, rowBytes, hIn + t0, rowBytes, sizeof(float) * (size_t) ns, rows,
-                                      cudaMemcpyHostToDevice, e->copyIn));
+            if (!pcm16) {
+                JB_CUDA(cudaMemcpy2DAsync(dBuf + t0, rowBytes, hIn + t0, rowBytes, sizeof(float) * (size_t) ns, rows,
+                                          cudaMemcpyHostToDevice, e->copyIn));
+            } else {
+                const int16_t* hIn16 = static_cast<const int16_t*>(h_in_v) + (size_t) c0 * e->nCh * n_samples;
+                JB_CUDA(cudaMemcpy2DAsync(dPcm + t0, rowBytes / 2, hIn16 + t0, rowBytes / 2, sizeof(int16_t) * (size_t) ns, rows,
+                                          cudaMemcpyHostToDevice, e->copyIn));
+            }
             JB_CUDA(cudaEventRecord(evIn, e->copyIn));
             JB_CUDA(cudaStreamWaitEvent(e->stream, evIn, 0));
+            if (pcm16 && jbk_launch_pcm16_to_float(dPcm + t0, dBuf + t0, (long long) rows, ns, n_samples, n_samples, e->stream) != 0)
+                return fail(JB_ERR_CUDA, "pcm16 -> float conversion kernel failed to launch");
             if ((rcLaunch = renderAutomated(e, dBuf + t0, dBuf + t0, ns, nc, c0, n_samples, blocksBase + firstBlock)) != JB_OK)
                 break;
+            if (pcm16 && jbk_launch_float_to_pcm16(dBuf + t0, dPcm + t0, (long long) rows, ns, n_samples, n_samples, e->stream) != 0)
+                return fail(JB_ERR_CUDA, "float -> pcm16 conversion kernel failed to launch");
             JB_CUDA(cudaEventRecord(evDone, e->stream));
             JB_CUDA(cudaStreamWaitEvent(e->copyOut, evDone, 0));
-            JB_CUDA(cudaMemcpy2DAsync(hOut + t0, rowBytes, dBuf + t0, rowBytes, sizeof(float) * (size_t) ns, rows,
-                                      cudaMemcpyDeviceToHost, e->copyOut));
+            if (!pcm16) {
+                JB_CUDA(cudaMemcpy2DAsync(hOut + t0, rowBytes, dBuf + t0, rowBytes, sizeof(float) * (size_t) ns, rows,
+                                          cudaMemcpyDeviceToHost, e->copyOut));
+            } else {
+                int16_t* hOut16 = static_cast<int16_t*>(h_out_v) + (size_t) c0 * e->nCh * n_samples;
+                JB_CUDA(cudaMemcpy2DAsync(hOut16 + t0, rowBytes / 2, dPcm + t0, rowBytes / 2, sizeof(int16_t) * (size_t) ns, rows,
+                                          cudaMemcpyDeviceToHost, e->copyOut));
+            }
         }
         JB_CUDA(cudaEventRecord(e->evOut[pass % nBuffers], e->copyOut));
         // (the slice events are re-recorded by the next pass; the waits above captured this pass's records)
@@ -1427,6 +1470,20 @@ int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples
         return rcLaunch;
     blocksGuard.value = blocksBase + totalBlocks;
     return JB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples)
+{
+    return processHost(e, h_in, h_out, n_samples, false);
+}
+
+int jb_process_host_pcm16(jb_engine* e, const int16_t* h_in, int16_t* h_out, int n_samples)
+{
+    return processHost(e, h_in, h_out, n_samples, true);
 }
 
 int jb_get_metrics(jb_engine* e, int slot, jb_metrics* out)

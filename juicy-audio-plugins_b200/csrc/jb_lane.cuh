@@ -149,9 +149,20 @@ struct AnaWalk {
         st.high = L.ld(base + AV_HIGH);
         st.cool = L.ldi(base + AV_COOLDOWN);
     }
-    __device__ __forceinline__ void step(float mono, const AnaCoef& c) { ana_step(st, acc, mono, c); }
+    // The walk goes in groups of up to four samples (a quad of the sweep): st.cool holds `rem` while a block is walked
+    // (AnaGroup, jb_device.cuh) and is turned back into the reference's counter by finish().
+    AnaGroup grp;
+    __device__ __forceinline__ void begin_block() { st.cool = st.cool - 1; }
+    __device__ __forceinline__ void group_begin() { grp.begin(st); }
+    __device__ __forceinline__ void step(int k, float mono, const AnaCoef& c)
+    {
+        grp.step(st, acc, k, mono, c);
+        ana_step_bands(st, acc, mono, c);
+    }
+    __device__ __forceinline__ void group_end(int count, const AnaCoef& c) { grp.end(st.cool, acc, count, c); }
     __device__ Metrics finish(const Lane& L, int base, const BlockStats& s, int n, const AnaCoef& c)
     {
+        st.cool = max(st.cool + 1, 0);
         st.repEma = L.ld(base + AV_REP_EMA);
         st.fatEma = L.ld(base + AV_FAT_EMA);
         const Metrics m = ana_finish(st, acc, s.sums(), n, c);
@@ -1108,8 +1119,12 @@ __device__ __forceinline__ void store8(float* p, const Quad& a, const Quad& b)
 // reference then loops over one channel only, its analyzer reads the right sample as the left one
 // (src/shared/JuicinessAnalyzer.cpp:55-60), and Width does no DSP at all (JuicyWidth/PluginProcessor.cpp:76-89).  A
 // compile-time variant so that the stereo kernels' code is untouched; only the generic kernel is instantiated for it.
-template <class Main, class Pre, bool MONO = false>
-__device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs)
+// REUSE_STATS: the block's state-independent sums are taken from *carry instead of being accumulated again (JuicyInfer with
+// trim = 0 dB leaves the buffer untouched between its two analyze() calls: JuicyInfer/PluginProcessor.cpp:78-80); otherwise
+// a non-null carry receives this sweep's sums.
+template <class Main, class Pre, bool MONO = false, bool REUSE_STATS = false>
+__device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs,
+                                      BlockStats* carry = nullptr)
 {
     const Lane L { a, clip };
     const int preSlot = mainSlot + 1;
@@ -1131,14 +1146,18 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
     if constexpr (Main::kHas) {
         mainPart.load(L, a.slot[mainSlot], n);
         post.load(L, a.slot[mainSlot].stateBase);
+        post.begin_block();
         mustWrite = mainPart.writes(a.in != a.out);
         if constexpr (MONO && Main::kMonoBypass)
             mustWrite = a.in != a.out;
     }
     if constexpr (Pre::kHas) {
         pre.load(L, a.slot[preSlot].stateBase);
+        pre.begin_block();
         prePart.load(L, a.slot[preSlot]);
     }
+    if constexpr (REUSE_STATS)
+        stats = *carry;
 
     if constexpr (Main::kSeqChannels) { // Motion: channel 0's block first
         Quad q = load4(srcL, 0, n, vec);
@@ -1161,6 +1180,10 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
         constexpr bool kSkipMain = MONO && (Main::kMonoBypass || Main::kSeqChannels); // Width: no DSP; Motion: no channel 1
         if (vec && !kSkipMain)
             mainPart.quad_begin();
+        if constexpr (Main::kHas)
+            post.group_begin();
+        if constexpr (Pre::kHas)
+            pre.group_begin();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (decltype(whole)::value || i + k < n) {
@@ -1170,16 +1193,24 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
                 if constexpr (MONO)
                     r = l; // `right != nullptr ? right[i] : l`
                 const float mono = 0.5f * (l + r);
-                stats.step(l, r, mono);
+                if constexpr (!REUSE_STATS)
+                    stats.step(l, r, mono);
                 if constexpr (Main::kHas)
-                    post.step(mono, ana);
+                    post.step(k, mono, ana);
                 if constexpr (Pre::kHas) {
-                    pre.step(mono, ana);
+                    pre.step(k, mono, ana);
                     prePart.step(l, r, mono);
                 }
                 ql.v[k] = l;
                 qr.v[k] = r;
             }
+        }
+        {
+            const int count = decltype(whole)::value ? 4 : min(4, n - i);
+            if constexpr (Main::kHas)
+                post.group_end(count, ana);
+            if constexpr (Pre::kHas)
+                pre.group_end(count, ana);
         }
         if (vec && !kSkipMain)
             mainPart.quad_end();
@@ -1347,6 +1378,9 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
         L.st(d.stateBase + AV_PRE_SCORE, m.score);
         prePart.finish(L, d, n);
     }
+    if constexpr (!REUSE_STATS)
+        if (carry != nullptr)
+            *carry = stats;
 }
 
 

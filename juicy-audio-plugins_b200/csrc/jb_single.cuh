@@ -21,6 +21,16 @@ __global__ void __launch_bounds__(JB_CTA_THREADS, MIN_CTAS) jb_single_kernel(con
     int blockAbs = a.histFirstBlock;
     for (int pos = 0; pos < a.nSamples; pos += a.blockSize, ++blockAbs) {
         const int n = min(a.blockSize, a.nSamples - pos);
+        if constexpr (std::is_same<Main, MainInfer>::value) {
+            // trim = 0 dB: applyGain(1) leaves the buffer as it is, so both analyze() calls of the block see the same
+            // samples and share their state-independent sums (a warp-uniform choice: the gain mode is a launch constant)
+            if (a.slot[0].c.infer.gainMode == 0) {
+                BlockStats sums;
+                sweep<MainNone, Pre>(a, clip, -1, pos, n, blockAbs, &sums);
+                sweep<Main, PreNone, false, true>(a, clip, 0, pos, n, blockAbs, &sums);
+                continue;
+            }
+        }
         sweep<MainNone, Pre>(a, clip, -1, pos, n, blockAbs);
         sweep<Main, PreNone>(a, clip, 0, pos, n, blockAbs);
     }

@@ -85,6 +85,7 @@ def lib():
         "jb_program_name": (cs, [vp, ci, ci]),
         "jb_process": (ci, [vp, vp, vp, ci]),
         "jb_process_host": (ci, [vp, vp, vp, ci]),
+        "jb_process_host_pcm16": (ci, [vp, vp, vp, ci]),
         "jb_synchronize": (ci, [vp]),
         "jb_set_stream": (ci, [vp, vp]),
         "jb_get_metrics": (ci, [vp, ci, vp]),
@@ -350,6 +351,17 @@ class BatchProcessor:
         out = np.empty_like(a)
         _check(lib().jb_process_host(self._h, a.ctypes.data, out.ctypes.data, a.shape[2]))
         return out
+
+    def processBlockPcm16(self, audio):
+        """Host audio as 16-bit PCM [n_clips][n_channels][n] (int16): converted on the device on the way in and out."""
+        a = np.ascontiguousarray(audio, dtype=np.int16)
+        assert a.shape[:2] == (self.n_clips, self.n_channels), a.shape
+        out = np.empty_like(a)
+        _check(lib().jb_process_host_pcm16(self._h, a.ctypes.data, out.ctypes.data, a.shape[2]))
+        return out
+
+    def process_host_pcm16_ptr(self, in_ptr, out_ptr, n_samples):
+        _check(lib().jb_process_host_pcm16(self._h, ctypes.c_void_p(int(in_ptr)), ctypes.c_void_p(int(out_ptr)), int(n_samples)))
 
     def process_host_ptr(self, in_ptr, out_ptr, n_samples):
         _check(lib().jb_process_host(self._h, ctypes.c_void_p(int(in_ptr)), ctypes.c_void_p(int(out_ptr)), int(n_samples)))
