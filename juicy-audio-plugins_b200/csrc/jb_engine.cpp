@@ -338,9 +338,21 @@ int resetState(jb_engine* e)
 int octetsFor(int kind, int nClips, int nSamples, bool mapped, bool exactMath)
 {
     static const int tileMode = [] { const char* v = std::getenv("JB_TILE"); return v == nullptr ? -1 : std::atoi(v); }();
+    // 3 = tile streaming through TMA (cp.async.bulk.tensor.3d, jb_lane.cuh): the warp's rows arrive without touching the
+    // LSU / L1TEX path, which bounds the light plugins on big batches.  It does what it was built for -- l1tex__throughput
+    // 82 % -> 25 % on JuicyCohere, 65536 clips -- and is still SLOWER there (20.9 -> 24 - 27 ms; 32768 clips 11.2 -> 16.7 ms;
+    // only at <= 16384 clips 8.5 -> 7.9 ms): with one row per clip a tile is 32 separate 64 / 128-byte row fetches, and the
+    // copy engine of an SM retires about one box row per 12 cycles whatever its length (the time follows rows / SM x 12
+    // cycles at every batch size and both tile widths: profiles/r02_tma.txt).  So it stays opt-in: JB_TMA=1 turns it on for
+    // light plugins, JB_TMA_MIN_CLIPS sets the smallest batch.
+    static const int tmaMode = [] { const char* v = std::getenv("JB_TMA"); return v == nullptr ? 0 : std::atoi(v); }();
+    static const int tmaMinClips = [] { const char* v = std::getenv("JB_TMA_MIN_CLIPS"); return v == nullptr ? 0 : std::atoi(v); }();
     if (mapped || kind == jb::kTexture || kind == jb::kMotion || (kind == jb::kPunch && exactMath))
         return 0;
     const bool tileOk = nClips % 32 == 0 && nSamples % 4 == 0;
+    const bool tma = tmaMode != 0 && nClips >= tmaMinClips;
+    if (tileOk && tma && !(tileMode > 0))
+        return 3;
     const bool tile = tileMode < 0 ? (kind == jb::kInfer && nClips >= 8192) : tileMode != 0;
     if (tileOk && tile)
         return 2;

@@ -158,10 +158,15 @@ struct ProcArgs {
     int exactMath;         // Saturator / Punch: glibc-exact tanh / pow (jb_libm.h) instead of the MUFU-based ones
     int vecOk;             // 16-byte vector path legal (alignment + sizes)
     int laneOnly;          // jb_set_path(JB_PATH_LANE): single-plugin launches take the lane kernels, not the clip-per-CTA one
-    int octets;            // lane kernel: 8 samples per trip + 32-byte stores (set for big batches of light chains, where
-                           // L2 sector throughput is the bound; costs registers, so not for Punch / Texture / Motion chains)
+    int octets;            // lane kernel: 1 = 8 samples per trip + 32-byte stores (big batches of light chains, where L2 sector
+                           // throughput is the bound; costs registers, so not for Punch / Texture / Motion chains); 2 = warp-
+                           // transposed tile streaming through cp.async; 3 = tile streaming through TMA (tmapIn below)
     AnaCoef ana;
     SlotDesc slot[JBK_MAX_CHAIN];
+    // octets == 3: CUtensorMap (128 bytes, opaque here) over the launch's input rows as a 3-D tensor {sample, channel, clip},
+    // box {16 samples, 1 channel, 32 clips}, 64-byte swizzle -- the warp's 32 rows of one channel arrive with ONE
+    // cp.async.bulk.tensor instruction (jb_lane.cuh: TMA tile streaming).  Filled by the launcher (jb_single_light.cu).
+    alignas(64) unsigned long long tmapIn[16];
 };
 
 #ifdef __cplusplus

@@ -1064,8 +1064,17 @@ __device__ __forceinline__ float4* lane_smem()
     extern __shared__ __align__(256) float4 jb_lane_dynamic_smem[]; // lane_smem_bytes(octets) at launch
     return jb_lane_dynamic_smem;
 }
+// TMA tile streaming (octets == 3): three stages x {left, right} tiles of 32 rows x 16 samples (2 KB each, the first one
+// 1024-byte aligned for the swizzle), then three mbarriers.  13 KB per warp: 16 warps per SM stay resident, like the
+// cp.async rings (with 32-sample tiles, 17 KB, only 12 fitted and a 65536-clip batch needed a second wave: +15 % time).
+constexpr int TMA_S = 16;                                        // samples per stage
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_TILE_BYTES = 32 * TMA_S * 4;
+constexpr int TMA_SMEM_BYTES = 2 * TMA_STAGES * TMA_TILE_BYTES + 64 + 1024; // + slack to align the first tile
 inline size_t lane_smem_bytes(int octets)
 {
+    if (octets == 3)
+        return (size_t) TMA_SMEM_BYTES;
     return octets == 2 ? (size_t) TILE_STAGES * TILE_STAGE_BYTES
                        : (size_t) JB_LANE_CTA_THREADS * 2 * (octets == 1 ? LF_RING : LF4_RING) * 16;
 }
@@ -1114,6 +1123,49 @@ __device__ __forceinline__ void store8(float* p, const Quad& a, const Quad& b)
                  : "memory");
 }
 
+// ---- sample access (v4): TMA tile streaming.
+// One row per lane means every 16-byte request of a warp touches 32 different lines; with cp.async rings that is 32 L1TEX
+// wavefronts per LDGSTS, and the L1TEX pipe -- not HBM, not instruction issue -- bounded the light kernels on big batches
+// (l1tex__throughput 78 - 82 % for Width / Cohere / Saturator, profiles/r02_c5_kernels_sections.txt).  Here the warp's 32
+// left rows (and its 32 right rows) of a 16-sample stretch arrive with ONE cp.async.bulk.tensor.3d each: the tensor map
+// views the audio as {sample, channel, clip}, the box is {16, 1, 32}, and the copy engine writes the tile
+// [clip][16 samples] into shared memory without touching the LSU / L1TEX path at all.  64-byte swizzle: the 16-byte
+// piece j of row r lands at r * 64 + ((j ^ ((r >> 1) & 3)) << 4), so the lanes of a quarter-warp, each reading piece j of
+// its own row, hit eight different bank groups.  Three stages, one mbarrier each; lane 0 issues two stages ahead, every
+// lane waits on the barrier's phase.  Stage g (counted over the whole kernel) uses buffer and barrier g % 3 in phase
+// (g / 3) & 1.
+__device__ __forceinline__ void tma_bar_init(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar)); }
+__device__ __forceinline__ void tma_bar_expect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t tma_tile_base() { return (lf_smem_u32(lane_smem()) + 1023u) & ~1023u; }
+// once per kernel, by the whole warp, before the first sweep
+__device__ __forceinline__ void tma_tiles_init()
+{
+    const uint32_t bars = tma_tile_base() + 2 * TMA_STAGES * TMA_TILE_BYTES;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < TMA_STAGES; ++i)
+            tma_bar_init(bars + 8 * i);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+
 // One sweep over one block of one clip.  mainSlot < 0 for sweep 0.
 // MONO: one-channel bus (isBusesLayoutSupported allows mono == mono, e.g. JuicyPunch/PluginProcessor.cpp:48-54).  The
 // reference then loops over one channel only, its analyzer reads the right sample as the left one
@@ -1124,7 +1176,7 @@ __device__ __forceinline__ void store8(float* p, const Quad& a, const Quad& b)
 // a non-null carry receives this sweep's sums.
 template <class Main, class Pre, bool MONO = false, bool REUSE_STATS = false>
 __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs,
-                                      BlockStats* carry = nullptr)
+                                      BlockStats* carry = nullptr, unsigned* tmaCount = nullptr)
 {
     const Lane L { a, clip };
     const int preSlot = mainSlot + 1;
@@ -1226,7 +1278,74 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
     };
     constexpr std::true_type kWhole {};
     constexpr std::false_type kRagged {};
-    if (vec && a.octets == 2 && !Main::kHeavy) {
+    if (vec && a.octets == 3 && !Main::kHeavy && tmaCount != nullptr) {
+        // TMA tile streaming (see above): 16 samples per stage, eight at a time through the lane's math, 32-byte stores
+        const uint32_t tiles = tma_tile_base();
+        const uint32_t bars = tiles + 2 * TMA_STAGES * TMA_TILE_BYTES;
+        const int lane = threadIdx.x;
+        const int clip0 = (int) (blockIdx.x * blockDim.x);         // first clip of this warp within the launch
+        const void* tmap = &a.tmapIn;
+        const int nStages = (n + TMA_S - 1) / TMA_S;
+        const unsigned g0 = *tmaCount;
+        const uint32_t rowOff = (uint32_t) lane * (TMA_S * 4u), sw = (uint32_t) ((lane >> 1) & 3);
+        const bool wide = ((reinterpret_cast<uintptr_t>(dstL) | reinterpret_cast<uintptr_t>(dstR)) & 31u) == 0;
+        unsigned buf = g0 % TMA_STAGES, par = (g0 / TMA_STAGES) & 1u;   // buffer / barrier and phase of the stage being consumed
+        unsigned ibuf = buf;                                        // ... of the stage being issued
+        auto issue = [&](int k) {
+            if (k < nStages && lane == 0) {
+                const uint32_t bar = bars + 8u * ibuf, dst = tiles + 2u * TMA_TILE_BYTES * ibuf;
+                tma_bar_expect(bar, 2u * TMA_TILE_BYTES);
+                tma_load_3d(dst, tmap, pos + TMA_S * k, 0, clip0, bar);
+                tma_load_3d(dst + TMA_TILE_BYTES, tmap, pos + TMA_S * k, 1, clip0, bar);
+            }
+            ibuf = ibuf + 1 == TMA_STAGES ? 0 : ibuf + 1;
+        };
+        issue(0);
+        issue(1);
+#pragma unroll 1
+        for (int k = 0; k < nStages; ++k) {
+            issue(k + 2);                                           // into the buffer stage k - 1 left (everybody is past it)
+            tma_bar_wait(bars + 8u * buf, par);
+            const uint32_t tL = tiles + 2u * TMA_TILE_BYTES * buf + rowOff, tR = tL + TMA_TILE_BYTES;
+            const int cnt = min(TMA_S, n - TMA_S * k);            // a multiple of 4
+#pragma unroll
+            for (int h = 0; h < TMA_S; h += 8) {
+                if (h + 8 <= cnt) {
+                    const uint32_t j0 = (uint32_t) (h >> 2);
+                    Quad l0 = lf_lds(tL + ((j0 ^ sw) << 4)), r0 = lf_lds(tR + ((j0 ^ sw) << 4));
+                    Quad l1 = lf_lds(tL + (((j0 + 1u) ^ sw) << 4)), r1 = lf_lds(tR + (((j0 + 1u) ^ sw) << 4));
+                    const int i = TMA_S * k + h;
+                    quad_math(l0, r0, i, kWhole);
+                    quad_math(l1, r1, i + 4, kWhole);
+                    if (mustWrite) {
+                        if (wide) {
+                            if (!Main::kSeqChannels)
+                                store8(dstL + i, l0, l1);
+                            store8(dstR + i, r0, r1);
+                        } else {
+                            if (!Main::kSeqChannels) {
+                                store4(dstL, i, n, vec, l0);
+                                store4(dstL, i + 4, n, vec, l1);
+                            }
+                            store4(dstR, i, n, vec, r0);
+                            store4(dstR, i + 4, n, vec, r1);
+                        }
+                    }
+                }
+            }
+            if (cnt & 4) { // one last quad of a ragged block
+                const uint32_t j0 = (uint32_t) ((cnt & ~7) >> 2);
+                Quad ql = lf_lds(tL + ((j0 ^ sw) << 4)), qr = lf_lds(tR + ((j0 ^ sw) << 4));
+                quad(ql, qr, TMA_S * k + (cnt & ~7), kWhole);
+            }
+            __syncwarp();   // every lane has read this stage's tiles
+            if (++buf == TMA_STAGES) {
+                buf = 0;
+                par ^= 1u;
+            }
+        }
+        *tmaCount = g0 + (unsigned) nStages;
+    } else if (vec && a.octets == 2 && !Main::kHeavy) {
         // Warp-transposed tile streaming (big batches of light plugins).  With one row per lane every 16-byte request of a
         // warp touches 32 different lines: 32 L1TEX wavefronts per LDGSTS / per store, and the L1TEX pipe, not HBM and
         // not instruction issue, was the bound (l1tex__throughput 80 %, profiles/r01_s6_single_ncu.md).  Here the warp loads

@@ -19,6 +19,9 @@ __global__ void __launch_bounds__(JB_CTA_THREADS, MIN_CTAS) jb_single_kernel(con
         return;
     const long long clip = a.clipMap != nullptr ? (long long) a.clipMap[lane] : lane;
     int blockAbs = a.histFirstBlock;
+    unsigned tmaCount = 0; // TMA stages loaded so far by this warp (octets == 3)
+    if (!Main::kHeavy && a.octets == 3)
+        tma_tiles_init();
     for (int pos = 0; pos < a.nSamples; pos += a.blockSize, ++blockAbs) {
         const int n = min(a.blockSize, a.nSamples - pos);
         if constexpr (std::is_same<Main, MainInfer>::value) {
@@ -26,13 +29,13 @@ __global__ void __launch_bounds__(JB_CTA_THREADS, MIN_CTAS) jb_single_kernel(con
             // samples and share their state-independent sums (a warp-uniform choice: the gain mode is a launch constant)
             if (a.slot[0].c.infer.gainMode == 0) {
                 BlockStats sums;
-                sweep<MainNone, Pre>(a, clip, -1, pos, n, blockAbs, &sums);
-                sweep<Main, PreNone, false, true>(a, clip, 0, pos, n, blockAbs, &sums);
+                sweep<MainNone, Pre>(a, clip, -1, pos, n, blockAbs, &sums, &tmaCount);
+                sweep<Main, PreNone, false, true>(a, clip, 0, pos, n, blockAbs, &sums, &tmaCount);
                 continue;
             }
         }
-        sweep<MainNone, Pre>(a, clip, -1, pos, n, blockAbs);
-        sweep<Main, PreNone>(a, clip, 0, pos, n, blockAbs);
+        sweep<MainNone, Pre>(a, clip, -1, pos, n, blockAbs, nullptr, &tmaCount);
+        sweep<Main, PreNone>(a, clip, 0, pos, n, blockAbs, nullptr, &tmaCount);
     }
 }
 
