@@ -1045,41 +1045,11 @@ int jbk_launch_coop(const ProcArgs* args, float* monoScratch, int numSMs, void* 
     ca.debugSkip = 0;
 #endif
     const int grid = ca.numGroups < numSMs ? ca.numGroups : numSMs;
-    // The analyzer lanes re-read the mono scratch one host block after the bulk warps wrote it; it is a ring that is
-    // overwritten all the time, so none of it ever has to reach HBM -- but with the per-access evict_last hint alone ~60 %
-    // of its lines were still written back (ncu: dram__bytes_write 2.9 GB against 1.6 GB of audio, profiles/
-    // r02_coop_exact_ncu.json).  A persisting-L2 access window over the ring for the duration of the launch keeps it
-    // resident; the window is taken down again right behind the kernel.  JB_COOP_L2_WINDOW=0 disables.
-    static const bool useWindow = [] { const char* v = getenv("JB_COOP_L2_WINDOW"); return v == nullptr || atoi(v) != 0; }();
-    bool windowSet = false;
-    if (useWindow) {
-        static thread_local int limitDev = -1;
-        int dev = 0, maxWindow = 0, maxPersist = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        const size_t ringBytes = sizeof(float) * (size_t) grid * CO_GMAX * (size_t) (args->chainLen + 1) * 2 * CO_BLOCKMAX;
-        if (maxWindow > 0 && maxPersist > 0) {
-            if (limitDev != dev) {
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t) maxPersist);
-                limitDev = dev;
-            }
-            cudaStreamAttrValue attr = {};
-            attr.accessPolicyWindow.base_ptr = monoScratch;
-            attr.accessPolicyWindow.num_bytes = ringBytes < (size_t) maxWindow ? ringBytes : (size_t) maxWindow;
-            attr.accessPolicyWindow.hitRatio = ringBytes <= (size_t) maxPersist ? 1.0f : (float) ((double) maxPersist / (double) ringBytes);
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            windowSet = cudaStreamSetAttribute((cudaStream_t) stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
-            cudaGetLastError();
-        }
-    }
+    // (A persisting-L2 access window over the mono scratch ring was tried: it cut the ring's write-back -- dram__bytes_write
+    // 2.9 -> 2.4 GB against 1.6 GB of audio -- without changing the kernel's time, but the L2 set-aside it needs is a
+    // device-wide limit that stays in force for every later kernel of the process: JuicyInfer on 65536 clips went 16.5 ->
+    // 44 ms behind it.  Not worth it; the per-access evict_last hints stay.)
     kernel<<<grid, CO_THREADS, sizeof(CoopSmem), (cudaStream_t) stream>>>(ca);
-    if (windowSet) {
-        cudaStreamAttrValue attr = {};
-        attr.accessPolicyWindow.num_bytes = 0;
-        cudaStreamSetAttribute((cudaStream_t) stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-    }
     jbk_note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
