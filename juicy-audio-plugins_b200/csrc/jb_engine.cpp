@@ -356,7 +356,10 @@ int octetsFor(int kind, int nClips, int nSamples, bool mapped, bool exactMath)
     const bool tile = tileMode < 0 ? (kind == jb::kInfer && nClips >= 8192) : tileMode != 0;
     if (tileOk && tile)
         return 2;
-    return nClips >= 32768 ? 1 : 0;
+    // 4 = 32-byte loads into registers two octets ahead (falls back to 1 inside the kernel where a row is not 32-byte
+    // aligned): half the L1TEX wavefronts of the cp.async rings.  JB_LDG256=0 keeps mode 1 (measured: profiles/r02_ldg256.txt).
+    static const int ldgMode = [] { const char* v = std::getenv("JB_LDG256"); return v == nullptr ? 1 : std::atoi(v); }();
+    return nClips >= 32768 ? (ldgMode ? 4 : 1) : 0;
 }
 
 int buildArgs(jb_engine* e, ProcArgs& a, const std::vector<jb::ParamSet>& params, const float* dIn, float* dOut, int nSamples,

@@ -160,7 +160,7 @@ struct ProcArgs {
     int laneOnly;          // jb_set_path(JB_PATH_LANE): single-plugin launches take the lane kernels, not the clip-per-CTA one
     int octets;            // lane kernel: 1 = 8 samples per trip + 32-byte stores (big batches of light chains, where L2 sector
                            // throughput is the bound; costs registers, so not for Punch / Texture / Motion chains); 2 = warp-
-                           // transposed tile streaming through cp.async; 3 = tile streaming through TMA (tmapIn below)
+                           // transposed tile streaming through cp.async; 3 = tile streaming through TMA (tmapIn below); 4 = 32-byte register loads
     AnaCoef ana;
     SlotDesc slot[JBK_MAX_CHAIN];
     // octets == 3: CUtensorMap (128 bytes, opaque here) over the launch's input rows as a 3-D tensor {sample, channel, clip},

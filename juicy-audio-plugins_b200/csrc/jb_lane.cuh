@@ -1076,7 +1076,7 @@ inline size_t lane_smem_bytes(int octets)
     if (octets == 3)
         return (size_t) TMA_SMEM_BYTES;
     return octets == 2 ? (size_t) TILE_STAGES * TILE_STAGE_BYTES
-                       : (size_t) JB_LANE_CTA_THREADS * 2 * (octets == 1 ? LF_RING : LF4_RING) * 16;
+                       : (size_t) JB_LANE_CTA_THREADS * 2 * ((octets == 1 || octets == 4) ? LF_RING : LF4_RING) * 16;
 }
 __device__ __forceinline__ void lf_sts(uint32_t addr, const Quad& q)
 {
@@ -1164,6 +1164,19 @@ __device__ __forceinline__ void tma_tiles_init()
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+}
+
+// Eight samples = one 32-byte sector per LOAD (LDG.256, sm_100), straight into registers, not allocated in L1 (each sample is
+// used once).  Counted in L1TEX wavefronts -- what bounds the light kernels on big batches -- a lane's eight samples cost
+// one request here against two 16-byte cp.async pieces plus two shared-memory reads through the lane ring.
+struct Oct { Quad a, b; };
+__device__ __forceinline__ Oct load8(const float* p)
+{
+    Oct o;
+    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(o.a.v[0]), "=f"(o.a.v[1]), "=f"(o.a.v[2]), "=f"(o.a.v[3]), "=f"(o.b.v[0]), "=f"(o.b.v[1]), "=f"(o.b.v[2]), "=f"(o.b.v[3])
+                 : "l"(p) : "memory");
+    return o;
 }
 
 // One sweep over one block of one clip.  mainSlot < 0 for sweep 0.
@@ -1434,6 +1447,46 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
                 qr = nr;
             }
             lf_wait<0>();
+        } else if (a.octets == 4 && (n & 7) == 0
+                   && ((reinterpret_cast<uintptr_t>(srcL) | reinterpret_cast<uintptr_t>(srcR) | reinterpret_cast<uintptr_t>(dstL)
+                        | reinterpret_cast<uintptr_t>(dstR)) & 31u) == 0) {
+            // Register prefetch, 32 bytes per load and per store: octet o + 2 of both rows is requested before octet o is
+            // worked on (two octets ~ 1000 instructions of this warp ahead of use, further than an HBM round trip at 16
+            // warps per SM), the loop is unrolled by two so that the two octets in flight sit in fixed registers.
+            const int nOct = n >> 3;
+            Oct l0 = load8(srcL), r0 = load8(srcR);
+            Oct l1 = l0, r1 = r0;
+            if (nOct > 1) {
+                l1 = load8(srcL + 8);
+                r1 = load8(srcR + 8);
+            }
+            auto work = [&](Oct& l, Oct& r, int o) {
+                quad_math(l.a, r.a, 8 * o, kWhole);
+                quad_math(l.b, r.b, 8 * o + 4, kWhole);
+                if (mustWrite) {
+                    if (!Main::kSeqChannels)
+                        store8(dstL + 8 * o, l.a, l.b);
+                    store8(dstR + 8 * o, r.a, r.b);
+                }
+            };
+#pragma unroll 1
+            for (int o = 0; o < nOct; o += 2) {
+                Oct cl = l0, cr = r0;
+                if (o + 2 < nOct) {
+                    l0 = load8(srcL + 8 * (o + 2));
+                    r0 = load8(srcR + 8 * (o + 2));
+                }
+                work(cl, cr, o);
+                if (o + 1 < nOct) {
+                    cl = l1;
+                    cr = r1;
+                    if (o + 3 < nOct) {
+                        l1 = load8(srcL + 8 * (o + 3));
+                        r1 = load8(srcR + 8 * (o + 3));
+                    }
+                    work(cl, cr, o + 1);
+                }
+            }
         } else {
             LaneFeedT<LF_RING> feed;
             feed.init(srcL, srcR, n);
