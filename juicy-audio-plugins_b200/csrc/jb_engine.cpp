@@ -357,8 +357,11 @@ int octetsFor(int kind, int nClips, int nSamples, bool mapped, bool exactMath)
     if (tileOk && tile)
         return 2;
     // 4 = 32-byte loads into registers two octets ahead (falls back to 1 inside the kernel where a row is not 32-byte
-    // aligned): half the L1TEX wavefronts of the cp.async rings.  JB_LDG256=0 keeps mode 1 (measured: profiles/r02_ldg256.txt).
-    static const int ldgMode = [] { const char* v = std::getenv("JB_LDG256"); return v == nullptr ? 1 : std::atoi(v); }();
+    // aligned): half the L1TEX wavefronts of the cp.async rings -- and slower all the same (JuicyCohere 65536 clips 21.2 ->
+    // 27.1 ms, 32768 clips 11.3 -> 16.4; Saturator 20.2 -> 22.2; profiles/r02_tma.txt): a warp issues in order, so the first
+    // use of a register still in flight stalls everything behind it, where a cp.async ring only ever blocks at its
+    // wait_group.  Opt-in: JB_LDG256=1.
+    static const int ldgMode = [] { const char* v = std::getenv("JB_LDG256"); return v == nullptr ? 0 : std::atoi(v); }();
     return nClips >= 32768 ? (ldgMode ? 4 : 1) : 0;
 }
 
