@@ -325,7 +325,10 @@ class Bench:
         n_clips, n = w["clips"], w["samples"]
         self.count = n_clips * 2 * n
         self.d_in = torch.empty(self.count, dtype=torch.float32, device="cuda")
-        self.d_out = torch.empty(self.count, dtype=torch.float32, device="cuda")
+        # JuicyInfer with trim = 0 dB leaves the audio untouched (JuicyInfer/PluginProcessor.cpp:79: applyGain(1) is a no-op):
+        # it scores in place, as processBlock does; every other workload renders out of place
+        self.in_place = w["chain"] == ["JuicyInfer"]
+        self.d_out = self.d_in if self.in_place else torch.empty(self.count, dtype=torch.float32, device="cuda")
         jb.synth_fill_device(self.d_in.data_ptr(), w["synth"], rank * n_clips, n_clips, 2, n, SAMPLE_RATE, device=local,
                              stream=stream.cuda_stream)
         self.eng = jb.BatchProcessor(w["chain"], n_clips, device=local)
@@ -475,6 +478,7 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         f_total, f_kernel, f_renders, _, _, _ = b.timed(max(2, steps // 2), 1, barrier)
         b.eng.set_math_mode("auto")
         fast = {"ms_per_step": f_total / max(2, steps // 2), "mean_render_ms": f_kernel / max(f_renders, 1)}
+    b_in_place = b.in_place
     times = torch.tensor([ms_total, e2e_s * 1000.0, kernel_ms, pcm_s * 1000.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -514,7 +518,7 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": count_bytes, "d2h_bytes_per_step": count_bytes + 64 * w["clips"],
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "host_in_place": e2e_in_place,
                 "api": "jb_process_host + jb_get_metrics (pinned host buffers)"},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "clocks": clocks, "device_in_place": b_in_place,
         "math": "auto (exact tanh / pow where a Punch / Saturator feeds another plugin)",
         "mean_juiciness": float(np.mean(rec_host[:, 13])) if rec_host is not None else None,
     }
