@@ -9,6 +9,7 @@
 #include "../../include/juicy_batch.h"
 #include "jb_kernels.h"
 #include "jb_params.h"
+#include "jb_partition.h"
 
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges cost nothing unless a profiler is attached
@@ -135,6 +136,7 @@ struct jb_engine {
     std::vector<int> clipMapHost;
     int* dClipMap = nullptr;
     bool groupsDirty = false;
+
     // Per-block automation: parameter changes taking effect at the start of an absolute block index
     struct AutoEvent { long long block; int slot; int index; float value; int first; int count; };
     std::vector<AutoEvent> schedule; // kept sorted by block (stable)
@@ -143,6 +145,8 @@ struct jb_engine {
     cudaEvent_t groupJoin[kGroupStreams] = {};
     cudaEvent_t groupFork = nullptr;
     std::vector<cudaEvent_t> pipeEvents; // [plugin][segment] of a pipelined chain render
+    jb::SmPartitions partitions;         // disjoint SM groups (green contexts) for parameter sets rendered side by side
+    int partitionsFor = 0;               // number of sets the partitions were made (or found unavailable) for
     int pipelineMaxClips = 16384;        // chains of at most this many clips are pipelined across plugins
 
     // Score gather across the GPUs of one box: an NCCL communicator, opaque here (jb_comm_* below)
@@ -208,6 +212,8 @@ void freeDevice(jb_engine* e)
     }
     if (e->groupFork) cudaEventDestroy(e->groupFork);
     e->groupFork = nullptr;
+    e->partitions.release();
+    e->partitionsFor = 0;
     for (cudaEvent_t ev : e->pipeEvents)
         cudaEventDestroy(ev);
     e->pipeEvents.clear();
@@ -577,15 +583,25 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
                 JB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                 e->pipeEvents.push_back(ev);
             }
+            // The L kernels are all different code.  Giving each plugin its own group of SMs (jb_partition.cpp), which doubles
+            // the speed of five Texture sets side by side, does NOT pay here: seven groups of 16 SMs leave 36 SMs idle and
+            // the plugins' costs are unequal (4096 clips 36.0 -> 42.0 ms, 16384 clips 82.8 -> 154 ms).  Opt-in: JB_PIPE_PARTITIONS=1.
+            static const bool pipeParts = [] { const char* v = std::getenv("JB_PIPE_PARTITIONS"); return v != nullptr && std::atoi(v) != 0; }();
+            if (pipeParts && e->partitionsFor != L) {
+                e->partitions.create(e->device, L);
+                e->partitionsFor = L;
+            }
+            const bool parted = pipeParts && e->partitions.count == L;
+            auto pipeStream = [&](int s) { return parted ? static_cast<cudaStream_t>(e->partitions.streams[s]) : e->groupStream[s]; };
             JB_CUDA(cudaEventRecord(e->groupFork, stream));
             for (int s = 0; s < L; ++s)
-                JB_CUDA(cudaStreamWaitEvent(e->groupStream[s], e->groupFork, 0));
+                JB_CUDA(cudaStreamWaitEvent(pipeStream(s), e->groupFork, 0));
             for (int k = 0; k * segBlocks < nBlocks; ++k) {
                 const int b0 = k * segBlocks;
                 const int t0 = b0 * B;
                 const int ns = std::min(a.nSamples - t0, segBlocks * B);
                 for (int s = 0; s < L; ++s) {
-                    cudaStream_t st = e->groupStream[s];
+                    cudaStream_t st = pipeStream(s);
                     if (s > 0)
                         JB_CUDA(cudaStreamWaitEvent(st, e->pipeEvents[(size_t) (s - 1) * K + k], 0));
                     if (int rc = launchOne(s, t0, ns, b0, st))
@@ -594,7 +610,7 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
                 }
             }
             for (int s = 0; s < L; ++s) {
-                JB_CUDA(cudaEventRecord(e->groupJoin[s], e->groupStream[s]));
+                JB_CUDA(cudaEventRecord(e->groupJoin[s], pipeStream(s)));
                 JB_CUDA(cudaStreamWaitEvent(stream, e->groupJoin[s], 0));
             }
         }
@@ -754,6 +770,22 @@ int renderClips(jb_engine* e, const float* dIn, float* dOut, int ns, int nc, lon
         JB_CUDA(cudaEventRecord(e->groupFork, e->stream));
     bool usedStream[kPool] = {};
     int next = 0;
+    // Three or more Texture sets side by side (BASELINE config 3: material = clip mod 5): every set gets its own stream and
+    // the small-code form of the two-lanes-per-clip kernel.  Unrolled, the kernels evict each other's loops from the SMs'
+    // instruction caches (1 / 2 / 3 / 5 at a time: 63 / 37 / 37 / 58 ms); rolled, one kernel alone is 2.3x slower but five at
+    // once take no longer than one: 24.7 ms (profiles/r02_tma.txt).  JB_SMALL_CODE=0 keeps the unrolled kernels, three at a time.
+    static const bool smallCodeOk = [] { const char* v = std::getenv("JB_SMALL_CODE"); return v == nullptr || std::atoi(v) != 0; }();
+    const bool manySets = !serial && e->chain.size() == 1 && e->chain[0] == jb::kTexture && e->nCh == 2 && e->groups.size() >= 3
+                          && e->groups.size() <= (size_t) kPool && nc <= 24576;
+    // Better still: every set on its own disjoint group of SMs (green contexts, jb_partition.cpp) -- then the full-speed
+    // unrolled kernels never meet in an instruction cache.  Falls back to the small-code kernels where partitions are
+    // unavailable.
+    if (manySets && e->partitionsFor != (int) e->groups.size()) {
+        e->partitions.create(e->device, (int) e->groups.size());
+        e->partitionsFor = (int) e->groups.size();
+    }
+    const bool partitioned = manySets && e->partitions.count == (int) e->groups.size();
+    const bool smallCode = smallCodeOk && manySets && !partitioned;
     for (const jb_engine::Group& g : e->groups) {
         ProcArgs a;
         if (g.first >= 0) {
@@ -775,23 +807,25 @@ int renderClips(jb_engine* e, const float* dIn, float* dOut, int ns, int nc, lon
         }
         cudaStream_t st = e->stream;
         if (!serial) {
-            st = e->groupStream[next];
+            st = partitioned ? static_cast<cudaStream_t>(e->partitions.streams[next]) : e->groupStream[next];
             if (!usedStream[next]) {
                 JB_CUDA(cudaStreamWaitEvent(st, e->groupFork, 0));
                 usedStream[next] = true;
             }
             // three launches side by side: more DIFFERENT kernels on the SMs at once cost more than they overlap (C3, five
             // Texture materials on 8192 clips: 1 stream 58 ms, 2 30.5, 3 27.1, 5 37.3 -- profiles/r01_s6_survey_single.txt)
-            static const int poolUse = [] { const char* v = std::getenv("JB_GROUP_STREAMS"); return v == nullptr ? 3 : std::min((int) jb_engine::kGroupStreams, std::max(1, std::atoi(v))); }();
+            static const int poolEnv = [] { const char* v = std::getenv("JB_GROUP_STREAMS"); return v == nullptr ? 0 : std::min((int) jb_engine::kGroupStreams, std::max(1, std::atoi(v))); }();
+            const int poolUse = partitioned ? (int) e->groups.size() : (poolEnv > 0 ? poolEnv : (smallCode ? (int) e->groups.size() : 3));
             next = (next + 1) % poolUse;
         }
+        a.smallCode = smallCode ? 1 : 0;
         if (int rc = launchKernels(e, a, st, serial))
             return rc;
     }
     if (!serial)
         for (int i = 0; i < kPool; ++i)
             if (usedStream[i]) {
-                JB_CUDA(cudaEventRecord(e->groupJoin[i], e->groupStream[i]));
+                JB_CUDA(cudaEventRecord(e->groupJoin[i], partitioned ? static_cast<cudaStream_t>(e->partitions.streams[i]) : e->groupStream[i]));
                 JB_CUDA(cudaStreamWaitEvent(e->stream, e->groupJoin[i], 0));
             }
     JB_CUDA(cudaEventRecord(stop, e->stream));

@@ -161,6 +161,9 @@ struct ProcArgs {
     int octets;            // lane kernel: 1 = 8 samples per trip + 32-byte stores (big batches of light chains, where L2 sector
                            // throughput is the bound; costs registers, so not for Punch / Texture / Motion chains); 2 = warp-
                            // transposed tile streaming through cp.async; 3 = tile streaming through TMA (tmapIn below); 4 = 32-byte register loads
+    int smallCode;         // two-lanes-per-clip Texture kernel: the quad's samples go through ONE copy of the sample code (launches of
+                           // several parameter sets side by side: different kernels on one SM evict each other's unrolled loops
+                           // from the instruction caches, profiles/r02_tma.txt)
     AnaCoef ana;
     SlotDesc slot[JBK_MAX_CHAIN];
     // octets == 3: CUtensorMap (128 bytes, opaque here) over the launch's input rows as a 3-D tensor {sample, channel, clip},

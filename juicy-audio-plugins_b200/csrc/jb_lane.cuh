@@ -542,6 +542,11 @@ struct MainTexture : MainBase {
     const TexCoef* c;
     float* wave;
     long long pitch;
+    // MAT >= 0: the material is a compile-time constant (one kernel per material: every `mat() == k` below folds away);
+    // MAT < 0 would take it from the coefficients at run time (tried: all parameter sets of a Texture engine in ONE launch
+    // with a warp-uniform material; its coefficients then come through LDC with a register index instead of constant-bank
+    // operands, and the launch took 35 ms against 24.7 for five small-code kernels side by side -- profiles/r02_tma.txt).
+    __device__ __forceinline__ int mat() const { return MAT >= 0 ? MAT : c->material; }
 
     __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int n)
     {
@@ -563,7 +568,7 @@ struct MainTexture : MainBase {
         rng1 = accA * rng0 + accC;
         wave = L.a.texWave + L.clip;
         pitch = L.a.clipPitch;
-        if (MAT == 1) {
+        if (mat() == 1) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 a1Rest[k] = metalA1(k, 1.0f); // bend = 1 + 0.09 * 0
@@ -612,7 +617,7 @@ struct MainTexture : MainBase {
     bool havePref = false;
     __device__ __forceinline__ void quad_begin()
     {
-        if (MAT != 2 && MAT != 3)
+        if (mat() != 2 && mat() != 3)
             return;
         const float* line0 = wave;
         const float* line1 = wave + (long long) c->waveSize * pitch;
@@ -667,7 +672,7 @@ struct MainTexture : MainBase {
         const TexCoef& k = *c;
         const float impact = f.impact, body = f.body, trail = f.trail, core = f.core;
         float shaped;
-        if (MAT == 0) { // gel :137-151
+        if (mat() == 0) { // gel :137-151
             const float zeta = jmap3(trail, 0.62f, 1.45f);
             const float cc = 2.0f * zeta * k.gelOmega;
             const float force = core * (0.52f + 0.62f * body);
@@ -676,7 +681,7 @@ struct MainTexture : MainBase {
             st.springPos += st.springVel;
             shaped = 0.48f * core + 1.85f * st.springPos;
             shaped = jblibm::tanhf_fdlibm(shaped * k.shapeGain); // the C library's own std::tanh: Texture's output feeds Width's threshold
-        } else if (MAT == 1) { // metal :152-169
+        } else if (mat() == 1) { // metal :152-169
             const float exc = core * (0.19f + 0.52f * impact);
             const float m0 = mode(st, 0, exc, a1[0]);
             const float m1 = mode(st, 1, exc, a1[1]);
@@ -685,10 +690,10 @@ struct MainTexture : MainBase {
             const float modes = m0 + m1 + m2 + m3;
             const float brightExcite = 0.03f * impact * (core - st.hp);
             shaped = (0.44f * core + 0.42f * modes + brightExcite) * k.shapeGain;
-        } else if (MAT == 2 || MAT == 3) { // wood :170-192, plastic :193-213
+        } else if (mat() == 2 || mat() == 3) { // wood :170-192, plastic :193-213
             const float exc = core * (k.excA + k.excB * impact);
             float newWave;
-            if (MAT == 2)
+            if (mat() == 2)
                 newWave = k.waveDamp * (0.62f * delayed + 0.38f * st.prevWave) + exc * (0.09f + 0.04f * body);
             else
                 newWave = k.waveDamp * (0.76f * delayed + 0.24f * st.prevWave) + 0.14f * exc;
@@ -755,7 +760,7 @@ struct MainTexture : MainBase {
         float* line0 = wave;
         float* line1 = wave + (long long) c->waveSize * pitch;
         float d0 = 0.0f, d1 = 0.0f;
-        if (MAT == 2 || MAT == 3) {
+        if (mat() == 2 || mat() == 3) {
             if (havePref) {
                 d0 = dq0[0]; dq0[0] = dq0[1]; dq0[1] = dq0[2]; dq0[2] = dq0[3];
                 d1 = dq1[0]; dq1[0] = dq1[1]; dq1[1] = dq1[2]; dq1[2] = dq1[3];
@@ -766,7 +771,7 @@ struct MainTexture : MainBase {
         }
         const Front f0 = front(l, ch0), f1 = front(r, ch1);
         float a1L[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, a1R[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-        if (MAT == 1) {
+        if (mat() == 1) {
             // The poles bend with the transient (`bend = 1 + 0.09 impact`, :157-158), which costs a std::cos per mode,
             // channel and sample -- but impact is exactly 0 whenever the sample does not exceed its envelope, and then
             // the angle is the block-constant one of load().  Taken only when that holds for every lane of the warp
@@ -788,7 +793,7 @@ struct MainTexture : MainBase {
         }
         l = back(l, ch0, rng0, line0, d0, f0, a1L);
         r = back(r, ch1, rng1, line1, d1, f1, a1R);
-        if (MAT == 2 || MAT == 3)
+        if (mat() == 2 || mat() == 3)
             waveIdx = waveIdx + 1 == c->waveSize ? 0 : waveIdx + 1;
     }
     __device__ __forceinline__ void store(const Lane& L, const SlotDesc& d)

@@ -154,6 +154,7 @@ struct AnaPair {
 template <bool EXACT>
 struct SatPair {
     static constexpr bool kHeavy = EXACT;
+    static constexpr bool kRolled = false;
     MainSat<EXACT> M;
     __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int ch)
     {
@@ -170,6 +171,7 @@ struct SatPair {
 template <bool EXACT>
 struct PunchPair {
     static constexpr bool kHeavy = true;
+    static constexpr bool kRolled = false;
     MainPunch<EXACT> M;
     __device__ __forceinline__ void load(const Lane& L, const SlotDesc& d, int ch)
     {
@@ -204,9 +206,15 @@ __device__ __forceinline__ uint32_t lcg_skip(uint32_t x, int n)
     return accA * x + accC;
 }
 
-template <int MAT>
+template <int MAT, bool ROLLED = false>
 struct TexPair {
     static constexpr bool kHeavy = true;
+    // ROLLED: the quad's four samples go through ONE copy of the sample code instead of four.  Alone that is 2.3x slower
+    // (gel 10.7 -> 24.2 ms: the unrolled quad overlaps a sample's analyzer with the next sample's DSP) -- but several
+    // DIFFERENT Texture kernels side by side evict each other's unrolled loops (~50 KB each) from the SM's instruction
+    // caches: five materials at once took 58 ms unrolled, 24.7 ms rolled, i.e. as long as one rolled kernel alone
+    // (profiles/r02_tma.txt).  Used for launches of three or more parameter sets rendered concurrently.
+    static constexpr bool kRolled = ROLLED;
     MainTexture<MAT> T; // this lane's channel lives in T.ch0 / T.rng0; T.waveIdx is kept in step by both lanes
     float* line;
     uint32_t rngStart;  // the instance's LCG state at the top of the block
@@ -223,7 +231,7 @@ struct TexPair {
         T.pitch = L.a.clipPitch;
         line = T.wave + (long long) ch * T.c->waveSize * T.pitch;
         havePref = false;
-        if (MAT == 1) {
+        if (T.mat() == 1) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 T.a1Rest[k] = T.metalA1(k, 1.0f);
@@ -238,7 +246,7 @@ struct TexPair {
     }
     __device__ __forceinline__ void quad_begin()
     {
-        if (MAT != 2 && MAT != 3)
+        if (T.mat() != 2 && T.mat() != 3)
             return;
         float a0[4], a1[4], fr[4];
 #pragma unroll
@@ -258,13 +266,13 @@ struct TexPair {
     __device__ __forceinline__ float step(unsigned mask, float x)
     {
         float delayed = 0.0f;
-        if (MAT == 2 || MAT == 3) {
+        if (T.mat() == 2 || T.mat() == 3) {
             delayed = dq[0];
             dq[0] = dq[1]; dq[1] = dq[2]; dq[2] = dq[3];
         }
         const typename MainTexture<MAT>::Front f = T.front(x, T.ch0);
         float a1[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-        if (MAT == 1) {
+        if (T.mat() == 1) {
             const bool rest = __all_sync(mask, f.impact == 0.0f); // see MainTexture::step
             if (rest) {
 #pragma unroll
@@ -278,7 +286,7 @@ struct TexPair {
             }
         }
         const float y = T.back(x, T.ch0, T.rng0, line, delayed, f, a1);
-        if (MAT == 2 || MAT == 3)
+        if (T.mat() == 2 || T.mat() == 3)
             T.waveIdx = T.waveIdx + 1 == T.c->waveSize ? 0 : T.waveIdx + 1;
         return y;
     }
@@ -364,13 +372,24 @@ __global__ void __launch_bounds__(JB_CTA_THREADS, MIN_CTAS) jb_pair_kernel(const
             lf_wait<PF_AHEAD - 1>();
             nxt = feed.read(q + 1);
             pm.quad_begin();
+            if constexpr (PM::kRolled) {
+#pragma unroll 1
+                for (int k = 0; k < 4; ++k) { // the quad rotates through cur.v[0]: no run-time register indexing
+                    const float y = pm.step(mask, cur.v[0]);
+                    const float o = xchg(mask, y);
+                    const float l = ch ? o : y, r = ch ? y : o;
+                    an.step(mask, ch, l, r, 0.5f * (l + r), y, ana);
+                    cur.v[0] = cur.v[1]; cur.v[1] = cur.v[2]; cur.v[2] = cur.v[3]; cur.v[3] = y;
+                }
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float y = pm.step(mask, cur.v[k]);
-                const float o = xchg(mask, y);
-                const float l = ch ? o : y, r = ch ? y : o;
-                an.step(mask, ch, l, r, 0.5f * (l + r), y, ana);
-                cur.v[k] = y;
+                for (int k = 0; k < 4; ++k) {
+                    const float y = pm.step(mask, cur.v[k]);
+                    const float o = xchg(mask, y);
+                    const float l = ch ? o : y, r = ch ? y : o;
+                    an.step(mask, ch, l, r, 0.5f * (l + r), y, ana);
+                    cur.v[k] = y;
+                }
             }
 #if defined(JB_PAIR_STORE_CS)
             asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(cur.v[0]), "f"(cur.v[1]), "f"(cur.v[2]), "f"(cur.v[3]) : "memory");
@@ -425,6 +444,15 @@ extern "C" int jbk_launch_pair(const ProcArgs* args, void* stream)
         case K_SAT: return (int) (args->exactMath ? launch_pair<SatPair<true>>(*args, st) : launch_pair<SatPair<false>>(*args, st));
         case K_PUNCH: return (int) (args->exactMath ? launch_pair<PunchPair<true>>(*args, st) : launch_pair<PunchPair<false>>(*args, st));
         case K_TEXTURE:
+            if (args->smallCode) {
+                switch (d.c.tex.material) {
+                    case 0: return (int) launch_pair<TexPair<0, true>>(*args, st);
+                    case 1: return (int) launch_pair<TexPair<1, true>>(*args, st);
+                    case 2: return (int) launch_pair<TexPair<2, true>>(*args, st);
+                    case 3: return (int) launch_pair<TexPair<3, true>>(*args, st);
+                    default: return (int) launch_pair<TexPair<4, true>>(*args, st);
+                }
+            }
             switch (d.c.tex.material) {
                 case 0: return (int) launch_pair<TexPair<0>>(*args, st);
                 case 1: return (int) launch_pair<TexPair<1>>(*args, st);
