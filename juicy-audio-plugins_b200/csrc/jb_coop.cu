@@ -46,8 +46,6 @@ constexpr int CO_NSIG = CO_MAXCHAIN + 1;
 // Warp roles (the SM's arbiter favours high warp ids, so the longest sequential chains sit on top):
 // [0] producer, [1 .. nBulk] bulk, then 2 scouts, nAna "band" analyzer warps and, highest, nAna
 // "envelope" analyzer warps (nAna = ceil(chainLen * groupClips / 32), decided per launch).
-constexpr int CO_W_PRODUCER = 0;
-constexpr int CO_W_BULK = 1;
 constexpr int CO_NSCOUT = CO_ROWS / 32;                 // 2 warps
 constexpr int CO_ANA_LANES = CO_GMAX * CO_MAXCHAIN;     // 96
 #ifndef JB_CO_WARPS
@@ -56,9 +54,15 @@ constexpr int CO_ANA_LANES = CO_GMAX * CO_MAXCHAIN;     // 96
 #ifndef JB_CO_ISOLATE
 #define JB_CO_ISOLATE 1   // 1: envelope warps alone on SM sub-partition 3; 0: roles by plain warp index
 #endif
+#ifndef JB_CO_BANDARRIVE
+#define JB_CO_BANDARRIVE 1 // band analyzer warps arrive at the hand-off barrier instead of waiting on it
+#endif
+#ifndef JB_CO_ROLLCH
+#define JB_CO_ROLLCH -1    // Punch's two channels through ONE copy of the chunk code (rolled loop of two trips): 1 always, 0 never,
+#endif                     // -1 with the exact routines only (their code is 3x the fast ones'; the fast kernel gains nothing)
 constexpr int CO_WARPS = JB_CO_WARPS;
 constexpr int CO_THREADS = CO_WARPS * 32;               // 672
-constexpr int CO_BAR_ANA = 1;                           // named barrier of the analyzer warps
+constexpr int CO_BAR_ANA = 1;                           // named barriers 1, 2 of the analyzer warps (by call parity)
 
 struct CoopSmem {
     // first, so that every 256-byte row is 256-byte aligned (the swizzle xors address bits 4..7)
@@ -184,6 +188,62 @@ template <bool EXACT>
 __device__ __forceinline__ void punch_chunk(float (&x)[CO_CH], float2 ck, const PunchCoef& c)
 {
     float fEnv = ck.x, sEnv = ck.y;
+    if (EXACT) {
+        // The lanes of a bulk warp hold consecutive chunks of ONE channel of ONE clip, so what a sample needs from the exact
+        // routines is nearly always the same for the whole warp, and two votes per chunk pick the cheap form for all of it:
+        //   * pow(0, e) = 0 (e > 0): no transient anywhere in the step -- the decay of a hit, silence, steady material --
+        //     skips the 8 powf calls;
+        //   * |wet * drive| <= 0.25 ln2 on all of them: tanhf's k = 0 form (jb_libm.h), under half the operations.
+        // Either form gives the C library's bits; the votes only decide how much is computed.  (Called by whole warps.)
+        float tr[CO_CH], sus[CO_CH], trMax = 0.0f;
+#pragma unroll
+        for (int i = 0; i < CO_CH; ++i) {
+            const float adry = fabsf(x[i]);
+            fEnv = c.omFast * adry + c.fastCoeff * fEnv;
+            sEnv = c.omSlow * adry + c.slowCoeff * sEnv;
+            tr[i] = jmaxf(0.0f, fEnv - sEnv);
+            sus[i] = jmaxf(0.0f, sEnv - tr[i] * 0.6f);
+            trMax = fmaxf(trMax, tr[i]);
+        }
+        float curve[CO_CH];
+        if (__any_sync(0xffffffffu, trMax > 0.0f)) {
+#pragma unroll
+            for (int i = 0; i < CO_CH; ++i)
+                curve[i] = jblibm::powf_glibc_pos(tr[i], c.curveExp);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CO_CH; ++i)
+                curve[i] = 0.0f;
+        }
+        float wet[CO_CH], th[CO_CH];
+        uint32_t dMax = 0;
+#pragma unroll
+        for (int i = 0; i < CO_CH; ++i) {
+            const float punchGain = 1.0f + c.punchK * curve[i];
+            const float sustainGain = 1.0f + c.sustainK * sus[i];
+            wet[i] = x[i] * punchGain * sustainGain;
+            th[i] = wet[i] * c.drive;
+            dMax = max(dMax, __float_as_uint(th[i]) & 0x7fffffffu);
+        }
+        if (__all_sync(0xffffffffu, dMax <= jblibm::kTanhSmallMaxBits)) {
+#pragma unroll
+            for (int i = 0; i < CO_CH; ++i)
+                th[i] = jblibm::tanhf_fdlibm_small(th[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CO_CH; ++i)
+                th[i] = jblibm::tanhf_fdlibm(th[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < CO_CH; ++i) {
+            const float dry = x[i];
+            const float soft = jblibm::fdiv(th[i], c.tanhDrive);
+            const float hard = jlimitf(-0.95f, 0.95f, wet[i] * c.hardK);
+            const float w = soft + c.clipAmt * (hard - soft);
+            x[i] = (dry + c.mix * (w - dry)) * c.outGain;
+        }
+        return;
+    }
     const float invTanhDrive = 1.0f / c.tanhDrive;
 #pragma unroll
     for (int i = 0; i < CO_CH; ++i) {
@@ -192,26 +252,15 @@ __device__ __forceinline__ void punch_chunk(float (&x)[CO_CH], float2 ck, const 
         fEnv = c.omFast * adry + c.fastCoeff * fEnv;
         sEnv = c.omSlow * adry + c.slowCoeff * sEnv;
         const float transient = jmaxf(0.0f, fEnv - sEnv);
-        if (EXACT) {
-            const float transientCurve = jblibm::powf_glibc_pos(transient, c.curveExp);
-            const float punchGain = 1.0f + c.punchK * transientCurve;
-            const float sustainGain = 1.0f + c.sustainK * jmaxf(0.0f, sEnv - transient * 0.6f);
-            float wet = dry * punchGain * sustainGain;
-            const float soft = jblibm::fdiv(jblibm::tanhf_fdlibm(wet * c.drive), c.tanhDrive);
-            const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
-            wet = soft + c.clipAmt * (hard - soft);
-            x[i] = (dry + c.mix * (wet - dry)) * c.outGain;
-        } else {
-            // from here on pointwise: fused multiply-adds (1e-7 relative, inside the sample tolerance)
-            const float transientCurve = pow_unit(transient, c.curveExp);
-            const float punchGain = fmaf(c.punchK, transientCurve, 1.0f);
-            const float sustainGain = fmaf(c.sustainK, jmaxf(0.0f, fmaf(-0.6f, transient, sEnv)), 1.0f);
-            float wet = dry * punchGain * sustainGain;
-            const float soft = tanh_fast(wet * c.drive) * invTanhDrive;
-            const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
-            wet = fmaf(c.clipAmt, hard - soft, soft);
-            x[i] = fmaf(c.mix, wet - dry, dry) * c.outGain;
-        }
+        // from here on pointwise: fused multiply-adds (1e-7 relative, inside the sample tolerance)
+        const float transientCurve = pow_unit(transient, c.curveExp);
+        const float punchGain = fmaf(c.punchK, transientCurve, 1.0f);
+        const float sustainGain = fmaf(c.sustainK, jmaxf(0.0f, fmaf(-0.6f, transient, sEnv)), 1.0f);
+        float wet = dry * punchGain * sustainGain;
+        const float soft = tanh_fast(wet * c.drive) * invTanhDrive;
+        const float hard = jlimitf(-0.95f, 0.95f, wet * c.hardK);
+        wet = fmaf(c.clipAmt, hard - soft, soft);
+        x[i] = fmaf(c.mix, wet - dry, dry) * c.outGain;
     }
 }
 
@@ -447,14 +496,7 @@ __device__ __forceinline__ void env_quad(AnaState& s, float& trAcc, float& gmax,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float a = fabsf(m[j]);
-        {
-            const bool up = a > s.sEnv;
-            s.sEnv = (up ? c.omaS : c.omrS) * a + (up ? c.aS : c.rS) * s.sEnv;
-        }
-        {
-            const bool up = a > s.lEnv;
-            s.lEnv = (up ? c.omaL : c.omrL) * a + (up ? c.aL : c.rL) * s.lEnv;
-        }
+        ana_env_update(s.sEnv, s.lEnv, a, c); // both envelopes' multiplies in packed halves (jb_device.cuh): same bits, 2 issue slots fewer
         const float tr = fmaxf(0.0f, s.sEnv - s.lEnv);
         trAcc += tr;
         gmax = fmaxf(gmax, tr);
@@ -471,14 +513,7 @@ __device__ __noinline__ void onset_replay(float sEnv, float lEnv, int& rem, int&
 #pragma unroll 1
     for (int j = 0; j < 8; ++j) {
         const float a = fabsf(m[j]);
-        {
-            const bool up = a > sEnv;
-            sEnv = (up ? c.omaS : c.omrS) * a + (up ? c.aS : c.rS) * sEnv;
-        }
-        {
-            const bool up = a > lEnv;
-            lEnv = (up ? c.omaL : c.omrL) * a + (up ? c.aL : c.rL) * lEnv;
-        }
+        ana_env_update(sEnv, lEnv, a, c);
         const float tr = fmaxf(0.0f, sEnv - lEnv);
         const bool onset = (tr > 0.045f) & (rem <= j);
         onsets += onset ? 1 : 0;
@@ -654,9 +689,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
     const bool onSeqPartition = ISOLATE ? (warp & 3) == 3 : warp >= CO_WARPS - nAna;
     const int seqIdx = ISOLATE ? warp >> 2 : warp - (CO_WARPS - nAna);  // index among the warps of sub-partition 3
     const int parIdx = ISOLATE ? warp - ((warp + 1) >> 2) : warp;       // index among the others
-    const int nPar = ISOLATE ? CO_WARPS - CO_WARPS / 4 : CO_WARPS - nAna;
     const int wScout = 1, wBand = wScout + CO_NSCOUT, wBulk = wBand + nAna;
-    const int nBulk = nPar - wBulk;
     const bool isProducerWarp = !onSeqPartition && parIdx == 0;
     const bool isScoutWarp = !onSeqPartition && parIdx >= wScout && parIdx < wBand;
     const bool isBandWarp = !onSeqPartition && parIdx >= wBand && parIdx < wBulk;
@@ -790,7 +823,21 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                     ana_walk<false>(ast, acc, feed, n, ana);
                 }
             }
+            // Band -> envelope hand-off of the call's two band energies.  The band lanes' walk is a third of the envelope
+            // lanes' (a 3-link chain against 4 links twice), so they only ARRIVE (bar.arrive, the PTX producer / consumer
+            // idiom) and go back to the bulk queue instead of sitting out the envelope walk; the envelope lanes wait.  Two
+            // barrier ids by call parity: at most two analyze() calls run between two __syncthreads, so a band warp that is
+            // a call ahead arrives on the other id, and bandAcc[hand] is not rewritten before the next __syncthreads.
+#if JB_CO_BANDARRIVE
+            if (isBandWarp) {
+                __threadfence_block();
+                asm volatile("bar.arrive %0, %1;" ::"r"(CO_BAR_ANA + hand), "r"(anaThreads) : "memory");
+            } else {
+                named_barrier(CO_BAR_ANA + hand, anaThreads);
+            }
+#else
             named_barrier(CO_BAR_ANA, anaThreads);
+#endif
             Metrics m {};
             if (isAna && isEnvWarp && !(dbgSkip & 32)) {
                 acc.lowAcc = sm.bandAcc[hand][anaIdx][0];
@@ -799,16 +846,22 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             }
             return m;
         };
-        auto analyze_pre = [&](int blk, int n) { // analyze(buffer) before the plugin's DSP (e.g. JuicyPunch/PluginProcessor.cpp:82)
-            const Metrics m = analyze(blk, n, anaSlot);
-            if (isAna && isEnvWarp)
-                preScore = m.score;
+        // phase 0: analyze(buffer) before the plugin's DSP (e.g. JuicyPunch/PluginProcessor.cpp:82); phase 1: after it (:114),
+        // then the mailboxes (:115-123).  ONE call site for every analyze() of the kernel (the loop in the step below): the
+        // walks are ~1100 instructions per inlined copy, there used to be four copies, and the exact-math instantiation's
+        // hot code had outgrown the SM's instruction cache (no_instruction was 25 % of its stall samples,
+        // profiles/r02_coop_icache.txt).
+        auto analyze_phase = [&](int blk, int n, int ph) {
+            const Metrics m = analyze(blk, n, anaSlot + ph);
+            if (isAna && isEnvWarp) {
+                if (ph == 0)
+                    preScore = m.score;
+                else
+                    publish_record(a, anaSlot, clip0 + anaClip, a.histFirstBlock + blk, m, preScore, 0.0f);
+            }
         };
-        auto analyze_post = [&](int blk, int n) { // ... and after it (:114), then the mailboxes (:115-123)
-            const Metrics m = analyze(blk, n, anaSlot + 1);
-            if (isAna && isEnvWarp)
-                publish_record(a, anaSlot, clip0 + anaClip, a.histFirstBlock + blk, m, preScore, 0.0f);
-        };
+        const int lastBlk = (a.nSamples + a.blockSize - 1) / a.blockSize - 1;
+        const int lastN = a.nSamples - lastBlk * a.blockSize;
 
         // ---- prologue: load step 0 and scout it
         __syncthreads(); // widthPos/widthCount visible; previous group's tiles are drained
@@ -820,33 +873,42 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
             scout_step(cur, gstep);
         __syncthreads();
 
-        // ---- main loop over steps
-        while (cur.valid) {
-            const Cursor nxt = cursor_next(a, cur);
+        // ---- main loop over steps, plus one trailing trip in which only the analyzers work (the last host block)
+        bool tailDone = false;
+        while (cur.valid || !tailDone) {
+            const bool tail = !cur.valid;
+            tailDone = tail;
+            const Cursor nxt = tail ? cur : cursor_next(a, cur);
             const unsigned step = gstep, slot = gstep & 1;
             const int blockPar = cur.blk & 1;
 
             if (isProducerWarp) {
                 if (lane == 0)
                     sm.claim[slot ^ 1] = 0; // the next step's work queue (nobody reads it before the barrier below)
-                if (nxt.valid) {
+                if (!tail && nxt.valid) {
                     bulk_wait_read(); // the store that last read the other slot has drained
                     issue_load(nxt, step + 1);
                 }
             } else {
                 if (isScoutWarp) {
-                    if (nxt.valid)
+                    if (!tail && nxt.valid)
                         scout_step(nxt, step + 1);
                 } else if (isEnvWarp || isBandWarp) {
                     // analyzers run one host block behind: pre-analysis of block blk-1 during the first
-                    // step of block blk, post-analysis during the second (or both, if blk is one step long)
-                    if (cur.blk > 0) {
-                        const bool single = cur.nBlk <= CO_T;
-                        if (cur.off == 0)
-                            analyze_pre(cur.blk - 1, a.blockSize);
-                        if (single || cur.off == CO_T)
-                            analyze_post(cur.blk - 1, a.blockSize);
+                    // step of block blk, post-analysis during the second (or both, if blk is one step long);
+                    // both calls of the last block in the trailing trip
+                    int blk = lastBlk, n = lastN, ph0 = 0, ph1 = 2;
+                    if (!tail) {
+                        blk = cur.blk - 1;
+                        n = a.blockSize;
+                        ph0 = cur.off == 0 ? 0 : 1;
+                        ph1 = (cur.nBlk <= CO_T || cur.off == CO_T) ? 2 : 1;
+                        if (cur.blk == 0)
+                            ph1 = ph0;
                     }
+#pragma unroll 1
+                    for (int ph = ph0; ph < ph1; ++ph)
+                        analyze_phase(blk, n, ph);
                 }
                 // ---- bulk work: the step's clips are a queue in shared memory, claimed one at a time.  The bulk warps
                 // live on it; scout and band warps join once their own (short) work of the step is done.  With the exact
@@ -856,7 +918,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                 // to it.  (Measured: the queue balances the step but the exact kernel stays dependency-bound -- 0.84 eligible
                 // warps per scheduler at 16 warps per SM, profiles/r02_coop_exact_ncu.json; 20 / 24 / 32 warps with fewer
                 // registers gave 7.0 / 6.9 / 7.6 ms against 7.3, and cost the fast instantiation 0.4 - 1.1 ms.)
-                const bool joins = isBulkWarp || isScoutWarp || isBandWarp || EXACT;
+                const bool joins = (isBulkWarp || isScoutWarp || isBandWarp || EXACT) && !tail;
                 if (joins) {
                 mbar_wait(&sm.bar[slot], (step >> 1) & 1);
                 const int nValid = max(0, min(CO_CH, cur.n - lane * CO_CH));
@@ -893,8 +955,22 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                             const float2 zero = make_float2(0.0f, 0.0f); // lanes past the step's end have no checkpoint
                             const float2 ckL = nValid > 0 ? sm.ckpt[slot][2 * ci][lane] : zero;
                             const float2 ckR = nValid > 0 ? sm.ckpt[slot][2 * ci + 1][lane] : zero;
+                            constexpr bool rollCh = JB_CO_ROLLCH < 0 ? EXACT : JB_CO_ROLLCH != 0;
+                            if (rollCh) {
+#pragma unroll 1
+                            for (int ch = 0; ch < 2; ++ch) { // one copy of the code: left, swap, right, swap back
+                                punch_chunk<EXACT>(l, ch == 0 ? ckL : ckR, d.c.punch);
+#pragma unroll
+                                for (int i = 0; i < CO_CH; ++i) {
+                                    const float t = l[i];
+                                    l[i] = r[i];
+                                    r[i] = t;
+                                }
+                            }
+                            } else {
                             punch_chunk<EXACT>(l, ckL, d.c.punch);
                             punch_chunk<EXACT>(r, ckR, d.c.punch);
+                            }
                         } else if (d.kind == K_WIDTH) {
                             int total = 0;
                             const int kStart = firstStep ? 0 : sm.widthCount[ci];
@@ -925,6 +1001,8 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                 }
             }
             __syncthreads();
+            if (tail)
+                break;
             if (isProducerWarp) {
                 for (int row = lane; row < rows; row += 32) {
                     float* dst = a.out + ((long long) (clip0 + (row >> 1)) * 2 + (row & 1)) * a.rowPitch + cur.pos;
@@ -938,10 +1016,6 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
 
         // ---- epilogue: analyzers finish the last host block; everyone stores state
         if (isEnvWarp || isBandWarp) {
-            const int lastBlk = (a.nSamples + a.blockSize - 1) / a.blockSize - 1;
-            const int pn = a.nSamples - lastBlk * a.blockSize;
-            analyze_pre(lastBlk, pn);
-            analyze_post(lastBlk, pn);
             if (isAna) {
                 const long long clip = clip0 + anaClip;
                 const int b = a.slot[anaSlot].stateBase;

@@ -22,8 +22,27 @@ int main(int argc, char** argv)
                 continue;
         }
         ++nTanh;
-        if (jblibm::f2u(tanhf(x)) != jblibm::f2u(jblibm::tanhf_fdlibm(x)))
+        const unsigned want = jblibm::f2u(tanhf(x));
+        if (want != jblibm::f2u(jblibm::tanhf_fdlibm(x)) || want != jblibm::f2u(jblibm::tanhf_fdlibm_full(x)))
             ++badTanh;
+        if ((jblibm::f2u(x) & 0x7fffffffu) <= jblibm::kTanhSmallMaxBits && want != jblibm::f2u(jblibm::tanhf_fdlibm_small(x)))
+            ++badTanh;
+    }
+    if (argc > 2) { // exhaustive: every float of magnitude < 80 (both signs), all three forms (a few minutes; run by hand)
+        long bad = 0, cnt = 0;
+        for (unsigned u = 0; u < 0x42a00000u; ++u) {
+            for (int sgn = 0; sgn < 2; ++sgn) {
+                const float x = jblibm::u2f(u | (sgn ? 0x80000000u : 0u));
+                const unsigned want = jblibm::f2u(tanhf(x));
+                bad += want != jblibm::f2u(jblibm::tanhf_fdlibm(x));
+                bad += want != jblibm::f2u(jblibm::tanhf_fdlibm_full(x));
+                if (u <= jblibm::kTanhSmallMaxBits)
+                    bad += want != jblibm::f2u(jblibm::tanhf_fdlibm_small(x));
+                ++cnt;
+            }
+        }
+        printf("{\"exhaustive_tanhf_checked\": %ld, \"mismatches\": %ld}\n", cnt, bad);
+        return bad != 0;
     }
     for (long i = 0; i < n; ++i) {
         s = s * 1664525u + 1013904223u;
