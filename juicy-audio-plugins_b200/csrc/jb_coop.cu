@@ -60,6 +60,14 @@ constexpr int CO_ANA_LANES = CO_GMAX * CO_MAXCHAIN;     // 96
 #ifndef JB_CO_ROLLCH
 #define JB_CO_ROLLCH -1    // Punch's two channels through ONE copy of the chunk code (rolled loop of two trips): 1 always, 0 never,
 #endif                     // -1 with the exact routines only (their code is 3x the fast ones'; the fast kernel gains nothing)
+#ifndef JB_CO_COLDROLL
+#define JB_CO_COLDROLL 1   // unroll factor of the exact routines' general-form loops (8 = fully unrolled): code size beats ILP here
+#endif
+#ifndef JB_CO_HOTROLL
+#define JB_CO_HOTROLL 2    // unroll factor of the k = 0 tanhf loop (8 / 4 / 2 / 1 measured alike on drum hits; mixed clips 8.1 / 7.2 / 7.0 / 6.9 ms)
+#endif
+constexpr int CO_COLDROLL = JB_CO_COLDROLL;
+constexpr int CO_HOTROLL = JB_CO_HOTROLL;
 constexpr int CO_WARPS = JB_CO_WARPS;
 constexpr int CO_THREADS = CO_WARPS * 32;               // 672
 constexpr int CO_BAR_ANA = 1;                           // named barriers 1, 2 of the analyzer warps (by call parity)
@@ -207,7 +215,7 @@ __device__ __forceinline__ void punch_chunk(float (&x)[CO_CH], float2 ck, const 
         }
         float curve[CO_CH];
         if (__any_sync(0xffffffffu, trMax > 0.0f)) {
-#pragma unroll
+#pragma unroll CO_COLDROLL
             for (int i = 0; i < CO_CH; ++i)
                 curve[i] = jblibm::powf_glibc_pos(tr[i], c.curveExp);
         } else {
@@ -226,11 +234,11 @@ __device__ __forceinline__ void punch_chunk(float (&x)[CO_CH], float2 ck, const 
             dMax = max(dMax, __float_as_uint(th[i]) & 0x7fffffffu);
         }
         if (__all_sync(0xffffffffu, dMax <= jblibm::kTanhSmallMaxBits)) {
-#pragma unroll
+#pragma unroll CO_HOTROLL
             for (int i = 0; i < CO_CH; ++i)
                 th[i] = jblibm::tanhf_fdlibm_small(th[i]);
         } else {
-#pragma unroll
+#pragma unroll CO_COLDROLL
             for (int i = 0; i < CO_CH; ++i)
                 th[i] = jblibm::tanhf_fdlibm(th[i]);
         }
@@ -918,7 +926,14 @@ __global__ void __launch_bounds__(CO_THREADS, 1) jb_coop_kernel(const __grid_con
                 // to it.  (Measured: the queue balances the step but the exact kernel stays dependency-bound -- 0.84 eligible
                 // warps per scheduler at 16 warps per SM, profiles/r02_coop_exact_ncu.json; 20 / 24 / 32 warps with fewer
                 // registers gave 7.0 / 6.9 / 7.6 ms against 7.3, and cost the fast instantiation 0.4 - 1.1 ms.)
-                const bool joins = (isBulkWarp || isScoutWarp || isBandWarp || EXACT) && !tail;
+#ifndef JB_CO_ENVJOIN
+#define JB_CO_ENVJOIN 1 // exact math: the envelope warps take bulk clips after their walk (1), never (0), or only while more than JB_CO_ENVJOIN clips are unclaimed (>1)
+#endif
+                bool joins = (isBulkWarp || isScoutWarp || isBandWarp || EXACT) && !tail;
+                if (JB_CO_ENVJOIN == 0 && isEnvWarp)
+                    joins = false;
+                if (JB_CO_ENVJOIN > 1 && isEnvWarp && joins)
+                    joins = G - *reinterpret_cast<volatile int*>(&sm.claim[slot]) > JB_CO_ENVJOIN;
                 if (joins) {
                 mbar_wait(&sm.bar[slot], (step >> 1) & 1);
                 const int nValid = max(0, min(CO_CH, cur.n - lane * CO_CH));
