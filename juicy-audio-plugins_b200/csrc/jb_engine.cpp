@@ -353,13 +353,20 @@ int octetsFor(int kind, int nClips, int nSamples, bool mapped, bool exactMath)
     // light plugins, JB_TMA_MIN_CLIPS sets the smallest batch.
     static const int tmaMode = [] { const char* v = std::getenv("JB_TMA"); return v == nullptr ? 0 : std::atoi(v); }();
     static const int tmaMinClips = [] { const char* v = std::getenv("JB_TMA_MIN_CLIPS"); return v == nullptr ? 0 : std::atoi(v); }();
-    if (mapped || kind == jb::kTexture || kind == jb::kMotion || (kind == jb::kPunch && exactMath))
-        return 0;
+    if (mapped || kind == jb::kTexture || kind == jb::kMotion || ((kind == jb::kPunch || kind == jb::kSaturator) && exactMath))
+        return 0; // the exact routines' code: four samples per trip is what fits the instruction cache (jb_kernels.cu)
     const bool tileOk = nClips % 32 == 0 && nSamples % 4 == 0;
     const bool tma = tmaMode != 0 && nClips >= tmaMinClips;
     if (tileOk && tma && !(tileMode > 0))
         return 3;
-    const bool tile = tileMode < 0 ? (kind == jb::kInfer && nClips >= 8192) : tileMode != 0;
+    // Round 2: with the tile loop's body rolled to eight samples per trip (jb_lane.cuh, JB_TILE_UNROLL = 1: the 16-sample body
+    // of a writer was 42 KB of code, past the SM's 32 KB instruction cache) the tile also wins for the plugins that store
+    // every sample from 16384 clips up: Saturator 65536 clips 20.1 -> 18.3 ms, Punch (fast) 23.1 -> 22.5, Width 28.4 -> 28.0,
+    // Cohere 16384 clips 8.5 -> 7.7 ms (profiles/r02_tile_rolled.txt).
+    static const int forced = [] { const char* v = std::getenv("JB_OCTETS"); return v == nullptr ? -1 : std::atoi(v); }();
+    if (forced >= 0 && (forced < 2 || tileOk))
+        return forced; // experiments: force one streaming mode
+    const bool tile = tileMode < 0 ? nClips >= (kind == jb::kInfer ? 8192 : 16384) : tileMode != 0;
     if (tileOk && tile)
         return 2;
     // 4 = 32-byte loads into registers two octets ahead (falls back to 1 inside the kernel where a row is not 32-byte

@@ -95,8 +95,11 @@ int envInt(const char* name, int dflt) { const char* v = getenv(name); return v 
 // measured in place (profiles/r01_s6_pair.txt, last block): Texture 8192 clips 1.6x faster in pairs, 16384 / 24576 1.07-1.1x,
 // 32768 0.87x; Saturator / Punch with the MUFU math 1.45x at 8192, ~1.1x at 16384 / 24576 (0.93x around 12288), 0.7x at
 // 32768 where the one-lane kernel switches to eight samples per trip; with the exact routines faster at every size
+// Round 2, Saturator with the exact routines: the one-lane kernel on FOUR samples per trip (its eight-sample body is 42 KB
+// of code, past the instruction cache: no_instruction led its stalls) is ahead of the pairs from 32768 clips up -- 18.3
+// against 21.3 ms there, 35.0 against 36.7 ms at 65536 (profiles/r02_tile_rolled.txt); Punch stays in pairs (35.9 / 37.8 ms).
 const int g_pairLimitTexture = envInt("JB_PAIR_LIMIT_TEXTURE", 24576), g_pairLimitExact = envInt("JB_PAIR_LIMIT_EXACT", 1 << 30),
-          g_pairLimitFast = envInt("JB_PAIR_LIMIT_FAST", 24576);
+          g_pairLimitExactSat = envInt("JB_PAIR_LIMIT_EXACT_SAT", 24576), g_pairLimitFast = envInt("JB_PAIR_LIMIT_FAST", 24576);
 // clip-per-CTA kernel up to this many clips (measured, profiles/r02_solo.txt: Saturator 592 clips 2.2 ms against 4.2 ms on two
 // lanes per clip, 1184 clips 4.4 against 4.2; JuicyInfer against the cooperative kernel alike): six CTAs per SM
 const int g_soloLimit = envInt("JB_SOLO_LIMIT", 888);
@@ -152,7 +155,8 @@ int jbk_launch_process(const ProcArgs* args, void* stream)
         // crossovers in profiles/r01_s6_pair.txt.  JB_PAIR=0 / 1 forces a choice.
         if (jbk_pair_supported(args)) {
             const int kind = args->slot[0].kind;
-            const int limit = kind == K_TEXTURE ? g_pairLimitTexture : (args->exactMath ? g_pairLimitExact : g_pairLimitFast);
+            const int limit = kind == K_TEXTURE ? g_pairLimitTexture
+                                                : (args->exactMath ? (kind == K_SATURATOR ? g_pairLimitExactSat : g_pairLimitExact) : g_pairLimitFast);
             const bool pair = g_pairMode < 0 ? args->nClips <= limit : g_pairMode != 0;
             if (pair)
                 return check((cudaError_t) jbk_launch_pair(args, stream), "jb_pair_kernel launch");

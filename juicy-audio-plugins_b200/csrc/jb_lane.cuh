@@ -1192,6 +1192,13 @@ __device__ __forceinline__ Oct load8(const float* p)
 // REUSE_STATS: the block's state-independent sums are taken from *carry instead of being accumulated again (JuicyInfer with
 // trim = 0 dB leaves the buffer untouched between its two analyze() calls: JuicyInfer/PluginProcessor.cpp:78-80); otherwise
 // a non-null carry receives this sweep's sums.
+// Unroll factor of the tile-streaming loop's two 8-sample halves: 2 = both inline (16 samples per body), 1 = rolled (8 per
+// body), 0 = one quad per trip.  Measured on B200 (profiles/r02_tile_rolled.txt): 1 is ahead for every light plugin -- the
+// body is what has to stay inside the instruction caches.
+#ifndef JB_TILE_UNROLL
+#define JB_TILE_UNROLL 1
+#endif
+constexpr int JB_TILE_UNROLL_N = JB_TILE_UNROLL;
 template <class Main, class Pre, bool MONO = false, bool REUSE_STATS = false>
 __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mainSlot, int pos, int n, int blockAbs,
                                       BlockStats* carry = nullptr, unsigned* tmaCount = nullptr)
@@ -1404,7 +1411,31 @@ __device__ __forceinline__ void sweep(const ProcArgs& a, long long clip, int mai
             lf_wait<2>();                            // stage k has landed
             __syncwarp();
             const uint32_t st = tileS + (uint32_t) slot * TILE_STAGE_BYTES;
-#pragma unroll
+            if constexpr (JB_TILE_UNROLL_N == 0) {
+                // one quad per trip of a rolled loop (the smallest body: it is the instruction caches, not the issue slots, that
+                // the long unrolled bodies run out of); the first quad of an octet waits in registers for the second, so rows
+                // still leave with 32-byte stores
+                Quad sl, sr;
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {
+                    Quad l0 = lf_lds(st + myL + h * 16), r0 = lf_lds(st + myR + h * 16);
+                    const int i = 16 * k + 4 * h;
+                    quad_math(l0, r0, i, kWhole);
+                    if (mustWrite) {
+                        if (!wide) {
+                            store4(dstL, i, n, vec, l0);
+                            store4(dstR, i, n, vec, r0);
+                        } else if (h & 1) {
+                            store8(dstL + i - 4, sl, l0);
+                            store8(dstR + i - 4, sr, r0);
+                        } else {
+                            sl = l0;
+                            sr = r0;
+                        }
+                    }
+                }
+            } else
+#pragma unroll JB_TILE_UNROLL_N
             for (int h = 0; h < 2; ++h) { // eight samples at a time; results leave with one 32-byte store per row
                 Quad l0 = lf_lds(st + myL + h * 32), r0 = lf_lds(st + myR + h * 32);
                 Quad l1 = lf_lds(st + myL + h * 32 + 16), r1 = lf_lds(st + myR + h * 32 + 16);
