@@ -156,7 +156,7 @@ int jbk_launch_process(const ProcArgs* args, void* stream)
         if (jbk_pair_supported(args)) {
             const int kind = args->slot[0].kind;
             const int limit = kind == K_TEXTURE ? g_pairLimitTexture
-                                                : (args->exactMath ? (kind == K_SATURATOR ? g_pairLimitExactSat : g_pairLimitExact) : g_pairLimitFast);
+                                                : (args->exactMath ? (kind == K_SAT ? g_pairLimitExactSat : g_pairLimitExact) : g_pairLimitFast);
             const bool pair = g_pairMode < 0 ? args->nClips <= limit : g_pairMode != 0;
             if (pair)
                 return check((cudaError_t) jbk_launch_pair(args, stream), "jb_pair_kernel launch");
