@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- channel-samples/s of the JuicySuite hot path on B200 (BASELINE.json metric).
 
-Workloads (BASELINE.json `configs`, shapes of SURVEY.md §8(d)); `--config` picks one, the default is
-  N = 1 : C2 = configs[1], JuicyPunch -> JuicyWidth on 4096 stereo drum-hit clips (1 s, 48 kHz, 512-sample blocks) --
-          the configuration the metric is quoted on; C1 / C3 / C4 and one GPU's C5 shard follow in `other_configs`,
-          each with its own device-resident time, e2e, cpu_baseline and clocks;
-  N > 1 : C5 = configs[4], the full 7-plugin chain, 32768 stereo clips per GPU (262144 at 8 GPUs), weak scaling.
+Workloads (BASELINE.json `configs`, shapes of SURVEY.md §8(d)); `--config` picks one.  The default at EVERY N is
+  C5 = configs[4], the full 7-plugin chain, 32768 stereo clips per GPU (262144 at 8 GPUs), weak scaling -- the one
+  configuration BASELINE.json's metric ("... at 1/2/4/8 B200") spans, so the N = 1, 2, 4, 8 lines are the same workload
+  per GPU and their ratio is the scaling.  At N = 1 the other four configurations follow in `other_configs` -- C2 =
+  configs[1] (JuicyPunch -> JuicyWidth on 4096 drum-hit clips, the round-1 headline) first, then C1 / C3 / C4 -- each
+  with its own device-resident time, roofline, e2e, cpu_baseline and clocks.
 Clips are independent plugin-instance chains, so rank r renders its own clips and the data path has no collective;
 the per-clip Juiciness records are gathered with ONE ncclAllGather per step issued by the library itself
 (jb_gather_records, NCCL resolved with dlopen), inside the timed region.
@@ -14,8 +15,10 @@ A step = prepareToPlay-reset + one render of the whole batch, out of place (ever
 126 MB L2, so no step sees a warm cache).
   value    : device-resident throughput (inputs already in HBM), CUDA events on the engine's stream, max over ranks
   e2e      : the same render through jb_process_host with pinned HOST buffers, H2D + D2H inside the timed region
-  roofline : algorithmic bytes per render / mean device duration of the render (CUDA events recorded by the library
-             around its launches on its own stream) vs MEASURED_PEAKS.json
+  roofline : the dominant kernel's algorithmic bytes per launch / its mean device duration (CUDA events recorded by the
+             library on its own stream: around the render, and -- for a chain that renders as one launch per plugin --
+             between the plugins' launches, jb_slot_time_ms) vs MEASURED_PEAKS.json; `step` beside it is the whole
+             render (all of the chain's launches) against the chain's algorithmic bytes
   cpu_baseline / --impl reference : the reference's own C++ processBlock (oracle/_ref; the C port when that build is
              absent) on the box's host cores, a bounded sample of the same workload.
 The default math mode (JB_MATH_AUTO) is measured: a Punch / Saturator that feeds another plugin runs the C library's own
@@ -281,7 +284,7 @@ def cpu_baseline(w, threads, override=0, passes=2):
 
 
 def pick_workload(args, world):
-    name = args.config or ("C2" if world <= 1 else "C5")
+    name = args.config or "C5"
     w = dict(WORKLOADS[name])
     if args.clips:
         w["clips"] = args.clips
@@ -365,6 +368,7 @@ class Bench:
             torch.cuda.synchronize()
             barrier()
             self.eng.kernel_time_ms()
+            self.eng.enable_slot_timing(True)
             launches0 = self.jb.launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
@@ -376,6 +380,8 @@ class Bench:
             barrier()
             ms_total = e0.elapsed_time(e1)
             kernel_ms, kernel_renders = self.eng.kernel_time_ms()
+            self.slot_times = self.eng.slot_times_ms()
+            self.eng.enable_slot_timing(False)
             launches = self.jb.launch_count() - launches0
             coop, lane = self.eng.path_launches()
         if self.flush is not None:
@@ -469,6 +475,7 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
     if rank == 0:
         sampler.start()
     ms_total, kernel_ms, kernel_renders, launches, coop, lane = b.timed(steps, warmup, barrier)
+    slot_times = list(b.slot_times)   # of the default math mode (the fast-math leg below times its own)
     e2e_s, rec_host, e2e_in_place = b.e2e(e2e_steps, barrier)
     pcm_s = b.e2e_pcm16(e2e_steps, barrier) if with_pcm else 0.0
     clocks = sampler.stop() if rank == 0 else None
@@ -477,7 +484,8 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         b.eng.set_math_mode("fast")
         f_total, f_kernel, f_renders, _, _, _ = b.timed(max(2, steps // 2), 1, barrier)
         b.eng.set_math_mode("auto")
-        fast = {"ms_per_step": f_total / max(2, steps // 2), "mean_render_ms": f_kernel / max(f_renders, 1)}
+        fast = {"ms_per_step": f_total / max(2, steps // 2), "mean_render_ms": f_kernel / max(f_renders, 1),
+                "per_plugin_ms": [ms / max(k, 1) for ms, k in b.slot_times]}
     b_in_place = b.in_place
     times = torch.tensor([ms_total, e2e_s * 1000.0, kernel_ms, pcm_s * 1000.0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -509,12 +517,33 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         except Exception:
             traffic = None
     count_bytes = ch_samples_rank * 4
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_launch": alg,
+                "mean_launch_ms": mean_render_ms, "launches_timed": kernel_renders, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+    if len(w["chain"]) > 1 and all(n > 0 for _, n in slot_times):
+        # the chain rendered as one launch per plugin: the roofline object is the DOMINANT kernel's (rank 0's events between
+        # the plugins' launches); the whole render -- all launches against the chain's algorithmic bytes -- goes in `step`
+        n_blocks = (w["samples"] + BLOCK - 1) // BLOCK
+        per = [{"plugin": p, "mean_launch_ms": ms / n, "launches_timed": n,
+                # every plugin of a chain reads and rewrites the batch in place; JuicyInfer (trim = 0 dB) only reads it
+                "algorithmic_bytes_per_launch": (4.0 if p == "JuicyInfer" else 8.0) * ch_samples_rank + 64.0 * w["clips"] * n_blocks}
+               for p, (ms, n) in zip(w["chain"], slot_times)]
+        for k in per:
+            k["achieved"] = k["algorithmic_bytes_per_launch"] / (k["mean_launch_ms"] / 1000.0) / 1e9
+            k["frac"] = k["achieved"] / peak
+        top = max(per, key=lambda k: k["mean_launch_ms"])
+        step = {"frac": achieved / peak, "achieved": achieved, "algorithmic_bytes": alg, "ms": mean_render_ms,
+                "launches": kernels_per_render, "share_of_step": top["mean_launch_ms"] / mean_render_ms}
+        math_kind = "exact tanhf / powf" if top["plugin"] in ("JuicyPunch", "JuicySaturator") else "default"
+        roofline = {"bound": "hbm", "achieved": top["achieved"], "peak": peak, "unit": "GB/s", "frac": top["frac"],
+                    "traffic": traffic, "kernel": "%s launch of the chain (jb_pair_kernel / jb_single_kernel, %s)" % (top["plugin"], math_kind),
+                    "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "mean_launch_ms": top["mean_launch_ms"],
+                    "launches_timed": top["launches_timed"], "peak_source": peak_src,
+                    "frac_of_nominal_8TBs": top["achieved"] / 8000.0, "step": step, "per_plugin": per}
     res = {
         "value": value, "unit": UNIT, "ms_per_step": ms_total / steps, "steps": steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": kernel_name, "algorithmic_bytes_per_launch": alg,
-                     "mean_launch_ms": mean_render_ms, "launches_timed": kernel_renders, "peak_source": peak_src,
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": count_bytes, "d2h_bytes_per_step": count_bytes + 64 * w["clips"],
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "host_in_place": e2e_in_place,
                 "api": "jb_process_host + jb_get_metrics (pinned host buffers)"},
@@ -529,6 +558,7 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
     if fast:
         res["fast_math"] = {"ms_per_step": fast["ms_per_step"], "value": ch_samples_rank / (fast["ms_per_step"] / 1000.0),
                             "mean_render_ms": fast["mean_render_ms"],
+                            "per_plugin_ms": dict(zip(w["chain"], fast["per_plugin_ms"])) if len(w["chain"]) > 1 else None,
                             "frac": alg / (fast["mean_render_ms"] / 1000.0) / 1e9 / peak,
                             "note": "jb_set_math_mode(JB_MATH_FAST): MUFU-based tanh / pow, not decision-safe for every clip"}
     return res
@@ -587,10 +617,12 @@ def run_engine_arm(args):
         if world == 1 and not args.no_survey and not args.config:
             # the other BASELINE.json configurations on this GPU, each measured like the headline (fewer steps)
             others = []
-            for other in ("C1", "C3", "C4", "C5"):
+            for other in ("C2", "C1", "C3", "C4"):
                 ow = dict(WORKLOADS[other])
                 try:
-                    r = measure(jb, torch, dist, ow, other, local, 0, 1, stream, 3, 3, 2, None, peak, peak_src, with_fast=(other == "C5"))
+                    o_steps = 10 if other == "C2" else 3
+                    r = measure(jb, torch, dist, ow, other, local, 0, 1, stream, o_steps, 3, 3 if other == "C2" else 2, None, peak, peak_src,
+                                with_fast=(other == "C2"), with_pcm=(other == "C2"))
                     r["config"] = workload_config(ow, other)
                     if not args.no_cpu:
                         r["cpu_baseline"] = cpu_baseline(ow, host_threads(), 0)
@@ -617,7 +649,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("engine", "reference"), default="engine")
     ap.add_argument("--config", choices=sorted(WORKLOADS), default=None,
-                    help="workload (default: C2 = BASELINE.json configs[1] at N = 1, C5 = configs[4] per GPU at N > 1)")
+                    help="workload (default: C5 = BASELINE.json configs[4], one 32768-clip shard per GPU, at every N)")
     ap.add_argument("--clips", type=int, default=0, help="override the clips per GPU of the workload")
     ap.add_argument("--samples", type=int, default=0, help="override the samples per clip of the workload")
     ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU sample (default: ~4 M channel-samples per host thread)")

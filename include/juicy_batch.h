@@ -291,6 +291,14 @@ long long jb_launch_count(void);
  * the sum over launches of (stop - start) CUDA events recorded on the engine's stream
  * around every launch, and the number of launches summed.  Synchronises the stream. */
 int jb_kernel_time_ms(jb_engine* e, double* ms, long long* launches);
+/* Per-plugin device time of a chain that renders as one launch per plugin (the lane-per-clip kernels on batches too
+ * large for the plugin pipeline): while enabled, an event is recorded on the render's stream between the plugins'
+ * launches.  jb_slot_time_ms returns, for chain slot `slot`, the time and the number of launches accumulated since
+ * its previous call for that slot (0 launches where the render took another path: cooperative kernel, pipelined
+ * chain, a single plugin -- jb_kernel_time_ms covers those).  Both synchronise the stream.  No counterpart in the
+ * reference; measurement only (bench.py's per-kernel roofline). */
+int jb_enable_slot_timing(jb_engine* e, int on);
+int jb_slot_time_ms(jb_engine* e, int slot, double* ms, long long* launches);
 
 /* Plumbing for callers without a CUDA runtime of their own (the ctypes tests, the C++
  * demo): page-locked host memory and raw device memory on `device`. */

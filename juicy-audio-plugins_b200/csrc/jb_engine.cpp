@@ -160,6 +160,16 @@ struct jb_engine {
     size_t timingUsed = 0;
     double kernelMs = 0.0;
     long long kernelLaunches = 0;
+
+    // Opt-in per-plugin timing of a chain rendered plugin by plugin (jb_enable_slot_timing / jb_slot_time_ms): one event
+    // before the first launch and one after each plugin's launch, on the render's stream
+    bool slotTiming = false;
+    std::vector<cudaEvent_t> slotEvents;   // pool
+    size_t slotEventsUsed = 0;
+    struct SlotMark { int slot; size_t evStart, evStop; };
+    std::vector<SlotMark> slotMarks;
+    double slotMs[JBK_MAX_CHAIN] = {};
+    long long slotLaunches[JBK_MAX_CHAIN] = {};
 };
 
 namespace {
@@ -237,6 +247,11 @@ void freeDevice(jb_engine* e)
     for (cudaEvent_t ev : e->timingEvents)
         cudaEventDestroy(ev);
     e->timingEvents.clear();
+    for (cudaEvent_t ev : e->slotEvents)
+        cudaEventDestroy(ev);
+    e->slotEvents.clear();
+    e->slotMarks.clear();
+    e->slotEventsUsed = 0;
     for (cudaEvent_t ev : e->sliceEvents)
         cudaEventDestroy(ev);
     e->sliceEvents.clear();
@@ -576,9 +591,33 @@ int launchKernels(jb_engine* e, const ProcArgs& a, cudaStream_t stream, bool all
         const bool onEngineStream = stream == e->stream && L <= jb_engine::kGroupStreams;
         const bool pipeline = onEngineStream && nBlocks >= 4 && (pipeMode < 0 ? a.nClips <= e->pipelineMaxClips : pipeMode != 0);
         if (!pipeline) {
-            for (int s = 0; s < L; ++s)
+            // opt-in: an event between the plugins' launches (bench.py's per-kernel roofline of a chain)
+            const bool marks = e->slotTiming && e->slotMarks.size() < 65536;
+            size_t prev = 0;
+            auto mark = [&](size_t* index) -> int {
+                if (e->slotEventsUsed == e->slotEvents.size()) {
+                    cudaEvent_t ev = nullptr;
+                    JB_CUDA(cudaEventCreate(&ev));
+                    e->slotEvents.push_back(ev);
+                }
+                *index = e->slotEventsUsed++;
+                JB_CUDA(cudaEventRecord(e->slotEvents[*index], stream));
+                return JB_OK;
+            };
+            if (marks)
+                if (int rc = mark(&prev))
+                    return rc;
+            for (int s = 0; s < L; ++s) {
                 if (int rc = launchOne(s, 0, a.nSamples, 0, stream))
                     return rc;
+                if (marks) {
+                    size_t now = 0;
+                    if (int rc = mark(&now))
+                        return rc;
+                    e->slotMarks.push_back({ s, prev, now });
+                    prev = now;
+                }
+            }
         } else {
             static const int segEnv = [] { const char* v = std::getenv("JB_PIPE_SEGMENTS"); return v == nullptr ? 32 : std::max(2, std::atoi(v)); }();
             const int K = std::min(segEnv, nBlocks / 2);
@@ -1411,15 +1450,58 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
         const char* v = std::getenv(name);
         return (size_t) (v ? std::max(1, std::atoi(v)) : (int) dflt) << 20;
     };
-    const size_t passBudget = envMiB("JB_HOST_PASS_MIB", 8192), sliceTarget = envMiB("JB_HOST_SLICE_MIB", 96);
+    // Geometry (measured: profiles/r02_e2e_geometry.txt).  One pass whenever the batch fits the device beside what the
+    // engine already holds (a second pass costs more than its share: the C5 shard in two passes of 8 GiB ran at 35 GB/s per
+    // direction, in one pass at 46); slices of at least three host blocks (a slice's 2-D copies move one row per (clip,
+    // channel), and the render launches of a one-block slice are mostly prologue); and the last slices halve down to one
+    // block, because nothing overlaps the final slice's render and download.
+    size_t passBudget = envMiB("JB_HOST_PASS_MIB", 32768);
+    const size_t sliceTarget = envMiB("JB_HOST_SLICE_MIB", 96);
+    {
+        size_t freeB = 0, totalB = 0;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+            const size_t held = e->stageBytes[0] + e->stageBytes[1] + e->stageBytes[2];
+            const size_t whole = clipBytes * (size_t) e->nClips;
+            const size_t avail = (size_t) ((double) (freeB + held) * 0.85);
+            if (whole > avail)                       // does not fit in one piece: two alternating buffers must
+                passBudget = std::min(passBudget, avail / 2);
+        } else {
+            cudaGetLastError();
+        }
+    }
     long long passClips = std::max<long long>(32, (long long) (passBudget / clipBytes) / 32 * 32);
     passClips = std::min<long long>(passClips, e->nClips);
     const int nPasses = (int) ((e->nClips + passClips - 1) / passClips);
     const int totalBlocks = (n_samples + e->blockSize - 1) / e->blockSize;
     const size_t blockBytesAllClips = sizeof(float) * (size_t) e->blockSize * (size_t) e->nCh * (size_t) passClips;
-    int sliceBlocks = (int) std::max<size_t>(1, sliceTarget / std::max<size_t>(1, blockBytesAllClips));
+    const int minSliceBlocks = [] { const char* v = std::getenv("JB_HOST_MIN_SLICE_BLOCKS"); return v ? std::max(1, std::atoi(v)) : 3; }();
+    const bool taper = [] { const char* v = std::getenv("JB_HOST_TAPER"); return v == nullptr || std::atoi(v) != 0; }();
+    int sliceBlocks = (int) std::max<size_t>((size_t) minSliceBlocks, sliceTarget / std::max<size_t>(1, blockBytesAllClips));
     sliceBlocks = std::min(sliceBlocks, totalBlocks);
-    const int nSlices = (totalBlocks + sliceBlocks - 1) / sliceBlocks;
+    // slice s covers host blocks [sliceFirst[s], sliceFirst[s + 1])
+    std::vector<int> sliceFirst;
+    {
+        std::vector<int> tail;                       // 1, 2, 4, ... blocks, walked from the end of the call
+        if (taper && totalBlocks >= 4 * sliceBlocks)
+            for (int len = 1; len < sliceBlocks; len *= 2)
+                tail.push_back(len);
+        int tailBlocks = 0;
+        for (int len : tail)
+            tailBlocks += len;
+        int b = 0;
+        for (; b + sliceBlocks <= totalBlocks - tailBlocks; b += sliceBlocks)
+            sliceFirst.push_back(b);
+        if (b < totalBlocks - tailBlocks) {          // ragged rest of the uniform part
+            sliceFirst.push_back(b);
+            b = totalBlocks - tailBlocks;
+        }
+        for (size_t i = tail.size(); i-- > 0;) {
+            sliceFirst.push_back(b);
+            b += tail[i];
+        }
+        sliceFirst.push_back(totalBlocks);
+    }
+    const int nSlices = (int) sliceFirst.size() - 1;
 
     if (e->copyIn == nullptr) {
         JB_CUDA(cudaStreamCreateWithFlags(&e->copyIn, cudaStreamNonBlocking));
@@ -1488,9 +1570,9 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
         if (pass >= nBuffers) // this buffer's previous pass has been downloaded
             JB_CUDA(cudaStreamWaitEvent(e->copyIn, e->evOut[pass % nBuffers], 0));
         for (int sl = 0; sl < nSlices; ++sl) {
-            const int firstBlock = sl * sliceBlocks;
+            const int firstBlock = sliceFirst[(size_t) sl];
             const int t0 = firstBlock * e->blockSize;
-            const int ns = std::min(n_samples - t0, sliceBlocks * e->blockSize);
+            const int ns = std::min(n_samples, sliceFirst[(size_t) sl + 1] * e->blockSize) - t0;
             cudaEvent_t evIn = e->sliceEvents[(size_t) 2 * sl], evDone = e->sliceEvents[(size_t) 2 * sl + 1];
             if (!pcm16) {
                 JB_CUDA(cudaMemcpy2DAsync(dBuf + t0, rowBytes, hIn + t0, rowBytes, sizeof(float) * (size_t) ns, rows,
@@ -1708,6 +1790,51 @@ int jb_kernel_time_ms(jb_engine* e, double* ms, long long* launches)
         *launches = e->kernelLaunches;
     e->kernelMs = 0.0;
     e->kernelLaunches = 0;
+    return JB_OK;
+}
+
+int jb_enable_slot_timing(jb_engine* e, int on)
+{
+    if (int rc = checkEngine(e))
+        return rc;
+    if (int rc = setDevice(e))
+        return rc;
+    JB_CUDA(cudaStreamSynchronize(e->stream));
+    e->slotTiming = on != 0;
+    e->slotMarks.clear();
+    e->slotEventsUsed = 0;
+    for (int s = 0; s < JBK_MAX_CHAIN; ++s) {
+        e->slotMs[s] = 0.0;
+        e->slotLaunches[s] = 0;
+    }
+    return JB_OK;
+}
+
+int jb_slot_time_ms(jb_engine* e, int slot, double* ms, long long* launches)
+{
+    if (int rc = checkEngine(e))
+        return rc;
+    if (slot < 0 || slot >= (int) e->chain.size())
+        return fail(JB_ERR_ARG, "jb_slot_time_ms: slot %d outside the chain", slot);
+    if (int rc = setDevice(e))
+        return rc;
+    if (!e->slotMarks.empty()) {
+        JB_CUDA(cudaStreamSynchronize(e->stream));
+        for (const jb_engine::SlotMark& m : e->slotMarks) {
+            float t = 0.0f;
+            JB_CUDA(cudaEventElapsedTime(&t, e->slotEvents[m.evStart], e->slotEvents[m.evStop]));
+            e->slotMs[m.slot] += (double) t;
+            ++e->slotLaunches[m.slot];
+        }
+        e->slotMarks.clear();
+        e->slotEventsUsed = 0;
+    }
+    if (ms)
+        *ms = e->slotMs[slot];
+    if (launches)
+        *launches = e->slotLaunches[slot];
+    e->slotMs[slot] = 0.0;
+    e->slotLaunches[slot] = 0;
     return JB_OK;
 }
 

@@ -104,6 +104,8 @@ def lib():
         "jb_copy_to_device": (ci, [ci, vp, vp, ctypes.c_size_t]),
         "jb_copy_to_host": (ci, [ci, vp, vp, ctypes.c_size_t]),
         "jb_kernel_time_ms": (ci, [vp, ctypes.POINTER(cd), ctypes.POINTER(cll)]),
+        "jb_enable_slot_timing": (ci, [vp, ci]),
+        "jb_slot_time_ms": (ci, [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(cll)]),
         "jb_set_path": (ci, [vp, ci]),
         "jb_set_math_mode": (ci, [vp, ci]),
         "jb_path_launches": (ci, [vp, ctypes.POINTER(cll), ctypes.POINTER(cll)]),
@@ -443,6 +445,20 @@ class BatchProcessor:
         n = ctypes.c_longlong()
         _check(lib().jb_kernel_time_ms(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def enable_slot_timing(self, on=True):
+        """Per-plugin timing of a chain rendered as one launch per plugin (jb_enable_slot_timing)."""
+        _check(lib().jb_enable_slot_timing(self._h, 1 if on else 0))
+
+    def slot_times_ms(self):
+        """[(milliseconds, launches)] per chain slot since the last call (jb_slot_time_ms)."""
+        out = []
+        for s in range(len(self.chain)):
+            ms = ctypes.c_double()
+            n = ctypes.c_longlong()
+            _check(lib().jb_slot_time_ms(self._h, s, ctypes.byref(ms), ctypes.byref(n)))
+            out.append((ms.value, n.value))
+        return out
 
 
 def shard_range(n_clips, rank, world):

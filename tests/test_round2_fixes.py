@@ -116,3 +116,62 @@ def test_latest_metrics_survive_prepare_to_play(jb):
     eng.reset()
     assert np.array_equal(eng.getLatestMetrics(0), after)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chain", [["JuicyPunch", "JuicyWidth"], ["JuicySaturator", "JuicyMotion", "JuicyCohere"]],
+                         ids=["punch-width", "sat-motion-cohere"])
+def test_host_slice_geometry_does_not_change_the_render(chain, jb, monkeypatch):
+    """jb_process_host cuts the call into time slices (>= 3 host blocks, the last ones halving down to one block,
+    JB_HOST_TAPER) -- state carries across the slices like across host callbacks, so every geometry renders the same bits
+    and the same records as one slice over the whole call."""
+    n_clips, n = 40, 31 * BLOCK + 100
+    clips = jb.synth_clips("mixed", 3, n_clips, n)
+    outs = []
+    # one slice; 6-block slices with the tapered tail (6 ... 6, 4, 2, 1); the same untapered; one block per slice
+    for env in ({"JB_HOST_SLICE_MIB": "4096"}, {"JB_HOST_SLICE_MIB": "1"}, {"JB_HOST_SLICE_MIB": "1", "JB_HOST_TAPER": "0"},
+                {"JB_HOST_SLICE_MIB": "1", "JB_HOST_MIN_SLICE_BLOCKS": "1", "JB_HOST_PASS_MIB": "1"}):
+        for k in ("JB_HOST_PASS_MIB", "JB_HOST_SLICE_MIB", "JB_HOST_TAPER", "JB_HOST_MIN_SLICE_BLOCKS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = jb.BatchProcessor(chain, n_clips)
+        eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+        out = eng.processBlock(clips)
+        rec = eng.getLatestMetrics(len(chain) - 1)
+        eng.close()
+        outs.append((out, rec))
+    for out, rec in outs[1:]:
+        assert np.array_equal(out, outs[0][0])
+        assert np.array_equal(rec, outs[0][1])
+
+
+@pytest.mark.gpu
+def test_slot_timing_reports_every_plugin_of_a_chain(jb):
+    """jb_enable_slot_timing / jb_slot_time_ms: one (time, launches) pair per plugin of a chain that renders as one launch
+    per plugin; nothing for a render that takes the cooperative kernel (jb_kernel_time_ms covers that one)."""
+    chain = ["JuicySaturator", "JuicyCohere", "JuicyInfer"]
+    n_clips, n = 64, 3 * BLOCK          # fewer than four host blocks: no plugin pipeline, one launch per plugin
+    d = jb.DeviceBuffer(n_clips * 2 * n * 4)
+    jb.synth_fill_device(d.ptr.value, "mixed", 0, n_clips, 2, n, SAMPLE_RATE, device=0, stream=0)
+    eng = jb.BatchProcessor(chain, n_clips)
+    eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+    eng.enable_slot_timing(True)
+    for _ in range(2):
+        eng.process_device(d.ptr.value, d.ptr.value, n)
+    times = eng.slot_times_ms()
+    assert [k for _, k in times] == [2, 2, 2]
+    assert all(ms > 0.0 for ms, _ in times)
+    assert [k for _, k in eng.slot_times_ms()] == [0, 0, 0]      # read once, then reset
+    eng.enable_slot_timing(False)
+    eng.process_device(d.ptr.value, d.ptr.value, n)
+    assert [k for _, k in eng.slot_times_ms()] == [0, 0, 0]
+    eng.close()
+    coop = jb.BatchProcessor(["JuicyPunch", "JuicyWidth"], n_clips)
+    coop.prepareToPlay(SAMPLE_RATE, BLOCK)
+    coop.enable_slot_timing(True)
+    coop.process_device(d.ptr.value, d.ptr.value, n)
+    if coop.path_launches()[0] > 0:
+        assert [k for _, k in coop.slot_times_ms()] == [0, 0]
+    coop.close()
+    d.free()
