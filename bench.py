@@ -14,7 +14,9 @@ the per-clip Juiciness records are gathered with ONE ncclAllGather per step issu
 A step = prepareToPlay-reset + one render of the whole batch, out of place (every input is far larger than the
 126 MB L2, so no step sees a warm cache).
   value    : device-resident throughput (inputs already in HBM), CUDA events on the engine's stream, max over ranks
-  e2e      : the same render through jb_process_host with pinned HOST buffers, H2D + D2H inside the timed region
+  e2e      : the same render through jb_process_host with pinned HOST buffers, H2D + D2H inside the timed region; every
+             step is timed on its own and the figure is the MEDIAN step (max over ranks per step) -- the boxes' host <->
+             device path is shared with other tenants and single steps scatter by tens of percent; mean / min / max beside it
   roofline : the dominant kernel's algorithmic bytes per launch / its mean device duration (CUDA events recorded by the
              library on its own stream: around the render, and -- for a chain that renders as one launch per plugin --
              between the plugins' launches, jb_slot_time_ms) vs MEASURED_PEAKS.json; `step` beside it is the whole
@@ -409,17 +411,40 @@ class Bench:
         if in_place:  # the warm-up overwrote the input: restore it, so the timed steps render the same audio
             jb._check(jb.lib().jb_copy_to_host(self.local, h_in.array.ctypes.data, self.d_in.data_ptr(), self.count * 4))
         torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
+        per_step = []
+        for _ in range(steps):   # every step timed on its own (barrier + synchronize on both sides)
+            barrier()
+            t0 = time.perf_counter()
             rec = one()
-        torch.cuda.synchronize()
-        secs = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            per_step.append(time.perf_counter() - t0)
         barrier()
+        # The floor under those steps on THIS box, now: the same bytes as two plain pinned copies, host -> device and
+        # device -> host at once (what jb_process_host would take if rendering cost nothing and needed no pipeline ramp).
+        floor = None
+        try:
+            t_in, t_out = torch.from_numpy(h_in.array.reshape(-1)), torch.from_numpy(h_out.array.reshape(-1))
+            s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+            best = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                barrier()
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s_up):
+                    self.d_out.copy_(t_in, non_blocking=True)
+                with torch.cuda.stream(s_down):
+                    t_out.copy_(self.d_in, non_blocking=True)
+                torch.cuda.synchronize()
+                best.append(time.perf_counter() - t0)
+            floor = min(best[1:])
+            barrier()
+        except Exception:
+            floor = None
+        self.pcie_floor_s = floor
         h_in.free()
         if h_out is not h_in:
             h_out.free()
-        return secs, rec, in_place
+        return per_step, rec, in_place
 
     def e2e_pcm16(self, steps, barrier):
         """The same through jb_process_host_pcm16: 16-bit PCM host buffers (what audio files hold), converted on the device;
@@ -442,17 +467,18 @@ class Bench:
         self.eng.process_host_pcm16_ptr(pcm.ctypes.data, pcm.ctypes.data, n)
         fill()
         torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
+        per_step = []
         for _ in range(steps):
+            barrier()
+            t0 = time.perf_counter()
             self.eng.reset()
             self.eng.process_host_pcm16_ptr(pcm.ctypes.data, pcm.ctypes.data, n)
             self.eng.getLatestMetrics(self.last_slot)
-        torch.cuda.synchronize()
-        secs = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            per_step.append(time.perf_counter() - t0)
         barrier()
         h.free()
-        return secs
+        return per_step
 
     def close(self):
         try:
@@ -476,8 +502,8 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         sampler.start()
     ms_total, kernel_ms, kernel_renders, launches, coop, lane = b.timed(steps, warmup, barrier)
     slot_times = list(b.slot_times)   # of the default math mode (the fast-math leg below times its own)
-    e2e_s, rec_host, e2e_in_place = b.e2e(e2e_steps, barrier)
-    pcm_s = b.e2e_pcm16(e2e_steps, barrier) if with_pcm else 0.0
+    e2e_steps_s, rec_host, e2e_in_place = b.e2e(e2e_steps, barrier)
+    pcm_steps_s = b.e2e_pcm16(e2e_steps, barrier) if with_pcm else [0.0] * e2e_steps
     clocks = sampler.stop() if rank == 0 else None
     fast = None
     if with_fast and world == 1:
@@ -487,10 +513,19 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         fast = {"ms_per_step": f_total / max(2, steps // 2), "mean_render_ms": f_kernel / max(f_renders, 1),
                 "per_plugin_ms": [ms / max(k, 1) for ms, k in b.slot_times]}
     b_in_place = b.in_place
-    times = torch.tensor([ms_total, e2e_s * 1000.0, kernel_ms, pcm_s * 1000.0], dtype=torch.float64, device="cuda")
+    floor_s = getattr(b, "pcie_floor_s", None)
+    times = torch.tensor([ms_total, kernel_ms] + [x * 1000.0 for x in e2e_steps_s] + [x * 1000.0 for x in pcm_steps_s]
+                         + [1000.0 * floor_s if floor_s else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, kernel_ms, pcm_ms = [float(x) for x in times.tolist()]
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)   # every step: the slowest rank
+    tl = [float(x) for x in times.tolist()]
+    ms_total, kernel_ms = tl[0], tl[1]
+    e2e_list, pcm_list = tl[2:2 + e2e_steps], tl[2 + e2e_steps:2 + 2 * e2e_steps]
+    floor_ms = tl[2 + 2 * e2e_steps] or None
+    # The host <-> device path of these boxes is shared with other tenants (single steps scatter by tens of percent,
+    # profiles/r02_e2e_geometry.txt): the end-to-end figure is taken from the MEDIAN step; mean, min and max stand beside it.
+    e2e_ms = float(np.median(e2e_list)) * e2e_steps
+    pcm_ms = float(np.median(pcm_list)) * e2e_steps
     b.close()
     if rank != 0:
         return None
@@ -546,6 +581,10 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": count_bytes, "d2h_bytes_per_step": count_bytes + 64 * w["clips"],
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "host_in_place": e2e_in_place,
+                "statistic": "median of the individually timed steps (max over ranks per step)",
+                "ms_per_step_mean": float(np.mean(e2e_list)), "ms_per_step_min": float(min(e2e_list)), "ms_per_step_max": float(max(e2e_list)),
+                "pcie_floor_ms": floor_ms, "pcie_floor_note": "the same bytes as two plain pinned copies (H2D and D2H at once, no render), "
+                                                              "measured in this process right after the steps; best of 2, max over ranks",
                 "api": "jb_process_host + jb_get_metrics (pinned host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks, "device_in_place": b_in_place,
         "math": "auto (exact tanh / pow where a Punch / Saturator feeds another plugin)",
@@ -553,6 +592,7 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
     }
     if with_pcm:
         res["e2e_pcm16"] = {"value": world * ch_samples_rank * e2e_steps / (pcm_ms / 1000.0), "unit": UNIT, "ms_per_step": pcm_ms / e2e_steps,
+                            "ms_per_step_mean": float(np.mean(pcm_list)), "ms_per_step_min": float(min(pcm_list)),
                             "h2d_bytes_per_step": count_bytes // 2, "d2h_bytes_per_step": count_bytes // 2 + 64 * w["clips"],
                             "api": "jb_process_host_pcm16 + jb_get_metrics (pinned 16-bit PCM host buffers, device-side conversion)"}
     if fast:
@@ -599,7 +639,7 @@ def run_engine_arm(args):
     name, w = pick_workload(args, world)
     stream = torch.cuda.Stream()
     peak, peak_src = measured_peak_gbs()
-    e2e_steps = max(1, min(args.steps, 5 if w["clips"] * w["samples"] > 1e9 else args.steps))
+    e2e_steps = max(1, min(args.steps, 7 if w["clips"] * w["samples"] > 1e9 else args.steps))
     res = measure(jb, torch, dist, w, name, local, rank, world, stream, args.steps, args.warmup, e2e_steps, comm_id, peak, peak_src,
                   with_fast=True, with_pcm=True)
 
@@ -621,7 +661,8 @@ def run_engine_arm(args):
                 ow = dict(WORKLOADS[other])
                 try:
                     o_steps = 10 if other == "C2" else 3
-                    r = measure(jb, torch, dist, ow, other, local, 0, 1, stream, o_steps, 3, 3 if other == "C2" else 2, None, peak, peak_src,
+                    o_e2e = {"C2": 9, "C1": 5, "C3": 5, "C4": 3}[other]
+                    r = measure(jb, torch, dist, ow, other, local, 0, 1, stream, o_steps, 3, o_e2e, None, peak, peak_src,
                                 with_fast=(other == "C2"), with_pcm=(other == "C2"))
                     r["config"] = workload_config(ow, other)
                     if not args.no_cpu:

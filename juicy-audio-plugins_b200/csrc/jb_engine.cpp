@@ -1450,11 +1450,12 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
         const char* v = std::getenv(name);
         return (size_t) (v ? std::max(1, std::atoi(v)) : (int) dflt) << 20;
     };
-    // Geometry (measured: profiles/r02_e2e_geometry.txt).  One pass whenever the batch fits the device beside what the
-    // engine already holds (a second pass costs more than its share: the C5 shard in two passes of 8 GiB ran at 35 GB/s per
-    // direction, in one pass at 46); slices of at least three host blocks (a slice's 2-D copies move one row per (clip,
-    // channel), and the render launches of a one-block slice are mostly prologue); and the last slices halve down to one
-    // block, because nothing overlaps the final slice's render and download.
+    // Geometry (measured: profiles/r02_e2e_geometry.txt).  ONE pass whenever the batch fits the device beside what the
+    // engine already holds: the C5 shard (12.6 GB) in two passes of 8 GiB ran at 35 GB/s per direction, in one pass at 47
+    // -- the PCIe full-duplex rate of the box.  Within a pass small slices win (nothing overlaps the first slice's upload
+    // and the last slice's render + download): one host block per slice on big batches; small batches keep several blocks
+    // per slice (JB_HOST_SLICE_MIB: a launch over one block of a few thousand clips is mostly prologue) and halve the last
+    // slices down to one block instead (JB_HOST_TAPER).
     size_t passBudget = envMiB("JB_HOST_PASS_MIB", 32768);
     const size_t sliceTarget = envMiB("JB_HOST_SLICE_MIB", 96);
     {
@@ -1474,7 +1475,7 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
     const int nPasses = (int) ((e->nClips + passClips - 1) / passClips);
     const int totalBlocks = (n_samples + e->blockSize - 1) / e->blockSize;
     const size_t blockBytesAllClips = sizeof(float) * (size_t) e->blockSize * (size_t) e->nCh * (size_t) passClips;
-    const int minSliceBlocks = [] { const char* v = std::getenv("JB_HOST_MIN_SLICE_BLOCKS"); return v ? std::max(1, std::atoi(v)) : 3; }();
+    const int minSliceBlocks = [] { const char* v = std::getenv("JB_HOST_MIN_SLICE_BLOCKS"); return v ? std::max(1, std::atoi(v)) : 1; }();
     const bool taper = [] { const char* v = std::getenv("JB_HOST_TAPER"); return v == nullptr || std::atoi(v) != 0; }();
     int sliceBlocks = (int) std::max<size_t>((size_t) minSliceBlocks, sliceTarget / std::max<size_t>(1, blockBytesAllClips));
     sliceBlocks = std::min(sliceBlocks, totalBlocks);

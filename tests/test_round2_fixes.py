@@ -122,9 +122,9 @@ def test_latest_metrics_survive_prepare_to_play(jb):
 @pytest.mark.parametrize("chain", [["JuicyPunch", "JuicyWidth"], ["JuicySaturator", "JuicyMotion", "JuicyCohere"]],
                          ids=["punch-width", "sat-motion-cohere"])
 def test_host_slice_geometry_does_not_change_the_render(chain, jb, monkeypatch):
-    """jb_process_host cuts the call into time slices (>= 3 host blocks, the last ones halving down to one block,
-    JB_HOST_TAPER) -- state carries across the slices like across host callbacks, so every geometry renders the same bits
-    and the same records as one slice over the whole call."""
+    """jb_process_host cuts the call into time slices of whole host blocks (JB_HOST_SLICE_MIB, the last ones halving down to
+    one block: JB_HOST_TAPER) and, beyond the pass budget, into clip ranges -- state carries across the slices like across
+    host callbacks, so every geometry renders the same bits and the same records as one slice over the whole call."""
     n_clips, n = 40, 31 * BLOCK + 100
     clips = jb.synth_clips("mixed", 3, n_clips, n)
     outs = []

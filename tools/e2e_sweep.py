@@ -39,7 +39,23 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--floor", action="store_true", help="also time the JuicyInfer-only render of the same buffers")
+    ap.add_argument("--smi-ms", type=int, default=0, help="poll nvidia-smi (clocks, power, throttle reasons) every N ms meanwhile, as bench.py does")
+    ap.add_argument("--bind", action="store_true", help="bind to the CPUs NVML reports as local to GPU 0 before allocating, as bench.py does")
     args = ap.parse_args()
+    if args.bind:
+        import pynvml
+        pynvml.nvmlInit()
+        mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(0), (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1} & os.sched_getaffinity(0)
+        print(json.dumps({"bind": sorted(cpus)[:4] + ["..."] + sorted(cpus)[-2:], "n": len(cpus), "allowed": len(os.sched_getaffinity(0))}))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    smi = None
+    if args.smi_ms:
+        import subprocess
+        smi = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                                "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                "--format=csv,noheader,nounits", "-lms", str(args.smi_ms)], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     jb = load_juicy_batch()
     chain = FULL if args.chain == "full" else args.chain.split(",")
     n_clips, n = args.clips, args.samples
@@ -94,6 +110,8 @@ def main():
     print(json.dumps({"wall_s": round(time.perf_counter() - t_start, 1)}))
     for _, e in engines:
         e.close()
+    if smi is not None:
+        smi.terminate()
     return 0
 
 
