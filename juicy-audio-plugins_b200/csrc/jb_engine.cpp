@@ -15,6 +15,7 @@
 #include <nvtx3/nvToolsExt.h> // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1420,6 +1421,26 @@ extern "C" int jbk_launch_float_to_pcm16(const float* src, int16_t* dst, long lo
 
 namespace {
 
+// Does a render leave the audio as it is?  A chain of JuicyInfer instances whose trim is 0 dB everywhere: applyGain(1) is a
+// no-op (JuicyInfer/PluginProcessor.cpp:79), the plugin only scores.  (Pending automation: conservatively no.)
+bool audioUntouched(const jb_engine* e)
+{
+    if (!e->schedule.empty())
+        return false;
+    for (int k : e->chain)
+        if (k != jb::kInfer)
+            return false;
+    const int nSets = 1 + (int) e->variants.size();
+    for (int set = 0; set < nSets; ++set)
+        for (const jb::ParamSet& p : paramsOfSet(e, set)) {
+            SlotCoef c;
+            jb::makeSlotCoef(p, e->sampleRate, &c);
+            if (c.infer.gainMode != 0)
+                return false;
+        }
+    return true;
+}
+
 // jb_process_host / jb_process_host_pcm16: host audio [clip][channel][sample] as fp32 or as 16-bit PCM (`pcm16`).
 int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, bool pcm16)
 {
@@ -1477,7 +1498,14 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
     const size_t blockBytesAllClips = sizeof(float) * (size_t) e->blockSize * (size_t) e->nCh * (size_t) passClips;
     const int minSliceBlocks = [] { const char* v = std::getenv("JB_HOST_MIN_SLICE_BLOCKS"); return v ? std::max(1, std::atoi(v)) : 1; }();
     const bool taper = [] { const char* v = std::getenv("JB_HOST_TAPER"); return v == nullptr || std::atoi(v) != 0; }();
-    int sliceBlocks = (int) std::max<size_t>((size_t) minSliceBlocks, sliceTarget / std::max<size_t>(1, blockBytesAllClips));
+    // A slice's 2-D copy moves one row per (clip, channel), and the copy engines retire rows at a bounded RATE: 65536 rows
+    // take ~2.7 ms upward whether they hold 1 KB or 2 KB (profiles/r02_e2e_timeline.txt), and 1 KB rows downward twice that.
+    // Rows of at least 2 KB (fp32) / 4 KB (16-bit PCM, which is render-bound and gains from longer launches as well: C5
+    // shard 1 / 3 / 4 / 8 blocks per slice 330 / 210 / 189 / 187 ms) keep the copies on the PCIe rate instead.
+    const size_t minRowBytes = pcm16 ? 4096 : 2048;
+    const size_t blockRowBytes = (size_t) e->blockSize * (pcm16 ? sizeof(int16_t) : sizeof(float));
+    const size_t rowBlocks = (minRowBytes + blockRowBytes - 1) / blockRowBytes;
+    int sliceBlocks = (int) std::max({ (size_t) minSliceBlocks, rowBlocks, sliceTarget / std::max<size_t>(1, blockBytesAllClips) });
     sliceBlocks = std::min(sliceBlocks, totalBlocks);
     // slice s covers host blocks [sliceFirst[s], sliceFirst[s + 1])
     std::vector<int> sliceFirst;
@@ -1538,6 +1566,10 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
         e->sliceEvents.push_back(ev);
     }
 
+    // In place on the host and nothing in the chain changes the audio (JuicyInfer, trim = 0 dB): the caller's buffer already
+    // holds the result, only the records come back -- half the PCIe traffic of a scoring run (BASELINE config 4).
+    // (fp32 buffers only: the 16-bit writer's rule turns a -32768 into -32767, so that path always writes back.)
+    const bool skipDownload = !pcm16 && h_in_v == h_out_v && audioUntouched(e);
     const long long blocksBase = e->blocksDone;
     // renderAutomated moves e->blocksDone while it walks the slices; whatever exit path is taken (a CUDA error return
     // included) the counter ends at the value the call began with, or past the whole render on success
@@ -1547,6 +1579,17 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
         ~BlocksGuard() { e->blocksDone = value; }
     } blocksGuard { e, blocksBase };
     int rcLaunch = JB_OK;
+    // JB_HOST_TRACE=file: the pipeline's timeline of this call (one line per slice: when the host thread had issued it,
+    // when its upload / render / download finished on the device), appended to `file`.  Diagnostic only.
+    const char* tracePath = std::getenv("JB_HOST_TRACE");
+    struct TraceRow { int pass, slice, blocks; double issuedMs; cudaEvent_t up, render, down; };
+    std::vector<TraceRow> trace;
+    cudaEvent_t traceStart = nullptr;
+    const auto hostT0 = std::chrono::steady_clock::now();
+    if (tracePath != nullptr) {
+        JB_CUDA(cudaEventCreate(&traceStart));
+        JB_CUDA(cudaEventRecord(traceStart, e->copyIn));
+    }
     // every pass walks the same stretch of time, so each starts from the parameters and schedule the call began with
     const bool replay = nPasses > 1 && !e->schedule.empty();
     const auto params0 = replay ? e->params : std::vector<jb::ParamSet>();
@@ -1584,6 +1627,13 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
                                           cudaMemcpyHostToDevice, e->copyIn));
             }
             JB_CUDA(cudaEventRecord(evIn, e->copyIn));
+            TraceRow row { pass, sl, sliceFirst[(size_t) sl + 1] - firstBlock, 0.0, nullptr, nullptr, nullptr };
+            if (tracePath != nullptr) {
+                JB_CUDA(cudaEventCreate(&row.up));
+                JB_CUDA(cudaEventCreate(&row.render));
+                JB_CUDA(cudaEventCreate(&row.down));
+                JB_CUDA(cudaEventRecord(row.up, e->copyIn));
+            }
             JB_CUDA(cudaStreamWaitEvent(e->stream, evIn, 0));
             if (pcm16 && jbk_launch_pcm16_to_float(dPcm + t0, dBuf + t0, (long long) rows, ns, n_samples, n_samples, e->stream) != 0)
                 return fail(JB_ERR_CUDA, "pcm16 -> float conversion kernel failed to launch");
@@ -1592,14 +1642,23 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
             if (pcm16 && jbk_launch_float_to_pcm16(dBuf + t0, dPcm + t0, (long long) rows, ns, n_samples, n_samples, e->stream) != 0)
                 return fail(JB_ERR_CUDA, "float -> pcm16 conversion kernel failed to launch");
             JB_CUDA(cudaEventRecord(evDone, e->stream));
+            if (tracePath != nullptr)
+                JB_CUDA(cudaEventRecord(row.render, e->stream));
             JB_CUDA(cudaStreamWaitEvent(e->copyOut, evDone, 0));
-            if (!pcm16) {
+            if (skipDownload) {
+                // nothing to bring back; copyOut still follows the renders, so the pass-buffer hand-over below holds
+            } else if (!pcm16) {
                 JB_CUDA(cudaMemcpy2DAsync(hOut + t0, rowBytes, dBuf + t0, rowBytes, sizeof(float) * (size_t) ns, rows,
                                           cudaMemcpyDeviceToHost, e->copyOut));
             } else {
                 int16_t* hOut16 = static_cast<int16_t*>(h_out_v) + (size_t) c0 * e->nCh * n_samples;
                 JB_CUDA(cudaMemcpy2DAsync(hOut16 + t0, rowBytes / 2, dPcm + t0, rowBytes / 2, sizeof(int16_t) * (size_t) ns, rows,
                                           cudaMemcpyDeviceToHost, e->copyOut));
+            }
+            if (tracePath != nullptr) {
+                JB_CUDA(cudaEventRecord(row.down, e->copyOut));
+                row.issuedMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hostT0).count();
+                trace.push_back(row);
             }
         }
         JB_CUDA(cudaEventRecord(e->evOut[pass % nBuffers], e->copyOut));
@@ -1608,6 +1667,26 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
     JB_CUDA(cudaStreamSynchronize(e->copyIn));
     JB_CUDA(cudaStreamSynchronize(e->stream));
     JB_CUDA(cudaStreamSynchronize(e->copyOut));
+    if (tracePath != nullptr) {
+        if (FILE* f = std::fopen(tracePath, "a")) {
+            std::fprintf(f, "# call: %d clips, %d samples, %d pass(es), %d slices; pass slice blocks issued_ms up_done_ms render_done_ms down_done_ms\n",
+                         e->nClips, n_samples, nPasses, nSlices);
+            for (const TraceRow& r : trace) {
+                float up = 0.0f, rd = 0.0f, dn = 0.0f;
+                cudaEventElapsedTime(&up, traceStart, r.up);
+                cudaEventElapsedTime(&rd, traceStart, r.render);
+                cudaEventElapsedTime(&dn, traceStart, r.down);
+                std::fprintf(f, "%d %d %d %.3f %.3f %.3f %.3f\n", r.pass, r.slice, r.blocks, r.issuedMs, up, rd, dn);
+            }
+            std::fclose(f);
+        }
+        for (const TraceRow& r : trace) {
+            cudaEventDestroy(r.up);
+            cudaEventDestroy(r.render);
+            cudaEventDestroy(r.down);
+        }
+        cudaEventDestroy(traceStart);
+    }
     if (rcLaunch != JB_OK)
         return rcLaunch;
     blocksGuard.value = blocksBase + totalBlocks;

@@ -175,3 +175,31 @@ def test_slot_timing_reports_every_plugin_of_a_chain(jb):
         assert [k for _, k in coop.slot_times_ms()] == [0, 0]
     coop.close()
     d.free()
+
+
+@pytest.mark.gpu
+def test_scoring_in_place_on_the_host_leaves_the_buffer_and_returns_the_same_records(jb):
+    """JuicyInfer with trim = 0 dB does not change the audio (applyGain(1), JuicyInfer/PluginProcessor.cpp:79): rendered in
+    place on the host, jb_process_host brings back the records only.  Same records as the out-of-place render, buffer
+    untouched; with a trim the download happens and the buffer changes."""
+    n_clips, n = 48, 9 * BLOCK + 17
+    clips = jb.synth_clips("mixed", 21, n_clips, n)
+
+    def render(in_place, trim):
+        eng = jb.BatchProcessor(["JuicyInfer"], n_clips)
+        eng.setParameter("trim", trim)
+        eng.prepareToPlay(SAMPLE_RATE, BLOCK)
+        buf = clips.copy()
+        out = buf if in_place else np.empty_like(buf)
+        eng.process_host_ptr(buf.ctypes.data, out.ctypes.data, n)
+        rec = eng.getLatestMetrics(0)
+        eng.close()
+        return out, rec
+
+    out_a, rec_a = render(False, 0.0)
+    out_b, rec_b = render(True, 0.0)
+    assert np.array_equal(out_a, clips) and np.array_equal(out_b, clips)
+    assert np.array_equal(rec_a, rec_b)
+    out_c, _ = render(True, -6.0)
+    out_d, _ = render(False, -6.0)
+    assert np.array_equal(out_c, out_d) and not np.array_equal(out_c, clips)

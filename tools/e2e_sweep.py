@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--extra", default="", help="comma list of NAME=VALUE environment settings swept as a third axis, '|' between alternatives")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--rounds", type=int, default=3)
+    ap.add_argument("--pcm16", action="store_true", help="jb_process_host_pcm16 on 16-bit host buffers (in place) instead of jb_process_host")
     ap.add_argument("--floor", action="store_true", help="also time the JuicyInfer-only render of the same buffers")
     ap.add_argument("--smi-ms", type=int, default=0, help="poll nvidia-smi (clocks, power, throttle reasons) every N ms meanwhile, as bench.py does")
     ap.add_argument("--bind", action="store_true", help="bind to the CPUs NVML reports as local to GPU 0 before allocating, as bench.py does")
@@ -71,6 +72,17 @@ def main():
         engines.append(("floor(Infer)", jb.BatchProcessor(["JuicyInfer"], n_clips, device=0)))
     for _, e in engines:
         e.prepareToPlay(48000.0, 512)
+    if args.pcm16:
+        import numpy as np
+        pcm = h.array.view(np.int16).reshape(-1)[:count]          # the first half of the float buffer, as int16 samples
+        step = 1 << 24
+        for i in range(0, count, step):                            # any 16-bit content will do for timing: reinterpret the floats' bits
+            pass
+        def call(e):
+            e.process_host_pcm16_ptr(pcm.ctypes.data, pcm.ctypes.data, n)
+    else:
+        def call(e):
+            e.process_host_ptr(h.array.ctypes.data, h2.array.ctypes.data, n)
     extras = [x for x in args.extra.split("|")] if args.extra else [""]
     combos = [(x, p, sl) for x in extras for p in args.pass_mib.split(",") for sl in args.slice_mib.split(",")]
     samples = {}
@@ -92,11 +104,11 @@ def main():
             for name, e in engines:
                 if rnd == 0:
                     e.reset()
-                    e.process_host_ptr(h.array.ctypes.data, h2.array.ctypes.data, n)   # staging allocation of this geometry
+                    call(e)   # staging allocation of this geometry
                 for _ in range(args.reps):
                     e.reset()
                     t0 = time.perf_counter()
-                    e.process_host_ptr(h.array.ctypes.data, h2.array.ctypes.data, n)
+                    call(e)
                     samples.setdefault((combo, name), []).append((time.perf_counter() - t0) * 1e3)
     for combo in combos:
         extra, p, sl = combo

@@ -2,7 +2,7 @@
 # coop_variants.sh NAME "-DFLAG=.. ..."  -- build juicy-audio-plugins_b200/build/variants/libjb_NAME.so: the product library with
 # csrc/jb_coop.cu compiled under extra -D flags (kernel-variant A/B runs: JUICY_BATCH_LIB=... python tools/chain_bench.py ...).
 set -e
-HERE=$(cd "$(dirname "$0")/.." && pwd)
+HERE=$(cd "$(dirname "$0")/../.." && pwd)
 PKG=$HERE/juicy-audio-plugins_b200
 name=$1; flags=$2
 mkdir -p $PKG/build/variants

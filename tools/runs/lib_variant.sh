@@ -1,7 +1,7 @@
 #!/bin/bash
 # lib_variant.sh NAME SRC.cu "-DFLAGS"  -- build/variants/libjb_NAME.so = the product library with csrc/SRC.cu recompiled under extra flags
 set -e
-HERE=$(cd "$(dirname "$0")/.." && pwd)
+HERE=$(cd "$(dirname "$0")/../.." && pwd)
 PKG=$HERE/juicy-audio-plugins_b200
 name=$1; src=$2; flags=$3
 mkdir -p $PKG/build/variants
