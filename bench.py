@@ -118,15 +118,16 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=100):
         self.index = index
+        self.interval_ms = interval_ms
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -503,9 +504,19 @@ def measure(jb, torch, dist, w, name, local, rank, world, stream, steps, warmup,
         sampler.start()
     ms_total, kernel_ms, kernel_renders, launches, coop, lane = b.timed(steps, warmup, barrier)
     slot_times = list(b.slot_times)   # of the default math mode (the fast-math leg below times its own)
+    # The end-to-end steps are polled once a second instead of ten times: with the 100 ms poll running, the same steps took
+    # 348 / 372 ms (median of 7) against 321 / 281 ms without it (profiles/r02_e2e_smi_poll.txt; every query takes driver
+    # locks that the pipeline's ~1000 copies, launches and event records per step also need).  JB_BENCH_SMI_E2E=0: no poll.
+    clocks = sampler.stop() if rank == 0 else None
+    slow = ClockSampler(local, 1000)
+    if rank == 0 and os.environ.get("JB_BENCH_SMI_E2E", "1") != "0":
+        slow.start()
     e2e_steps_s, rec_host, e2e_in_place = b.e2e(e2e_steps, barrier)
     pcm_steps_s = b.e2e_pcm16(e2e_steps, barrier) if with_pcm else [0.0] * e2e_steps
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and slow.proc is not None:
+        c2 = slow.stop()
+        clocks["e2e_region"] = {"sm_mhz": c2.get("sm_mhz"), "samples": c2.get("samples", 0), "reasons": c2.get("reasons", []), "interval_ms": 1000}
+        clocks["reasons"] = sorted(set(clocks.get("reasons", [])) | (set(c2.get("reasons", [])) - {"no samples"}))
     fast = None
     if with_fast and world == 1:
         b.eng.set_math_mode("fast")
