@@ -24,7 +24,8 @@ def _engine(jb, plugin, n_clips, path, math="auto", settings=None, program=None,
 
 
 @pytest.mark.parametrize("plugin,math,program", [("JuicySaturator", "fast", 0), ("JuicySaturator", "exact", 3), ("JuicyInfer", "auto", 0),
-                                                 ("JuicyInfer", "auto", 2), ("JuicyInfer", "auto", 4)])
+                                                 ("JuicyInfer", "auto", 2), ("JuicyInfer", "auto", 4),
+                                                 ("JuicyCohere", "auto", 0)])
 def test_solo_kernel_equals_lane_kernels_and_oracle(plugin, math, program, jb, port):
     n_clips, n = 37, 6 * BLOCK + 132          # ragged last block (132 = 4 * 33)
     clips = jb.synth_clips("mixed", 5, n_clips, n)
@@ -45,6 +46,35 @@ def test_solo_kernel_equals_lane_kernels_and_oracle(plugin, math, program, jb, p
     for c in range(0, n_clips, 6):
         p = port.PortPlugin(plugin)
         p.set_program(program)
+        p.prepare()
+        ref_a, h_a = p.process(clips[c][:, :cut])
+        ref_b, h_b = p.process(clips[c][:, cut:])
+        assert_samples_close(outs["solo"][c], np.concatenate([ref_a, ref_b], axis=1), "clip %d" % c)
+        assert_records_close(hs[:, c], np.concatenate([h_a, h_b]), "clip %d records" % c)
+    solo.close()
+    lane.close()
+
+
+def test_solo_kernel_cohere_learning_targets_across_calls(jb, port):
+    """JuicyCohere on the few-streams kernel with `learn` on: the block pre-pass moves the three band targets every block
+    (JuicyCohere/PluginProcessor.cpp:78-84) and they persist across calls; contextfit (the record's aux field) follows."""
+    n_clips, n = 11, 7 * BLOCK
+    clips = jb.synth_clips("mixed", 9, n_clips, n)
+    settings = {"learn": 1.0, "match": 0.8, "tail": 0.5, "decay": 0.6}
+    solo = _engine(jb, "JuicyCohere", n_clips, "auto", settings=settings)
+    lane = _engine(jb, "JuicyCohere", n_clips, "lane", settings=settings)
+    cut = 3 * BLOCK
+    outs = {}
+    for name, eng in (("solo", solo), ("lane", lane)):
+        outs[name] = np.concatenate([eng.processBlock(clips[:, :, :cut]), eng.processBlock(clips[:, :, cut:])], axis=2)
+    assert np.array_equal(outs["solo"].view(np.uint32), outs["lane"].view(np.uint32))
+    hs, hl = solo.getHistory(0), lane.getHistory(0)
+    assert_records_close(hs, hl, "solo vs lane records")
+    assert np.array_equal(hs[:, :, 14], hl[:, :, 14])          # contextfit: the same operations on the same sums
+    for c in range(0, n_clips, 3):
+        p = port.PortPlugin("JuicyCohere")
+        for k, v in settings.items():
+            p.set_param(k, v)
         p.prepare()
         ref_a, h_a = p.process(clips[c][:, :cut])
         ref_b, h_b = p.process(clips[c][:, cut:])
