@@ -100,9 +100,10 @@ int envInt(const char* name, int dflt) { const char* v = getenv(name); return v 
 // against 21.3 ms there, 35.0 against 36.7 ms at 65536 (profiles/r02_tile_rolled.txt); Punch stays in pairs (35.9 / 37.8 ms).
 const int g_pairLimitTexture = envInt("JB_PAIR_LIMIT_TEXTURE", 24576), g_pairLimitExact = envInt("JB_PAIR_LIMIT_EXACT", 1 << 30),
           g_pairLimitExactSat = envInt("JB_PAIR_LIMIT_EXACT_SAT", 24576), g_pairLimitFast = envInt("JB_PAIR_LIMIT_FAST", 24576);
-// clip-per-CTA kernel up to this many clips (measured, profiles/r02_solo.txt: Saturator 592 clips 2.2 ms against 4.2 ms on two
-// lanes per clip, 1184 clips 4.4 against 4.2; JuicyInfer against the cooperative kernel alike): six CTAs per SM
-const int g_soloLimit = envInt("JB_SOLO_LIMIT", 888);
+// clip-per-CTA kernel up to this many clips: eight per SM, two rounds of resident CTAs (measured at the end of round 2,
+// profiles/r02_solo_clocks.txt: 1184 clips Saturator 3.2 ms against 4.2 on the lane kernels, Infer 2.8 / 4.7, Cohere 4.6 / 6.3;
+// 1480 clips 4.6 / 4.2, 4.2 / 4.7, 6.2 / 6.3)
+const int g_soloLimit = envInt("JB_SOLO_LIMIT", 1184);
 const bool g_forceGeneric = [] { const char* v = getenv("JB_LANE_GENERIC"); return v != nullptr && atoi(v) != 0; }();
 
 int check(cudaError_t e, const char* what)
