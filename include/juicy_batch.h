@@ -297,6 +297,10 @@ int jb_kernel_time_ms(jb_engine* e, double* ms, long long* launches);
  * its previous call for that slot (0 launches where the render took another path: cooperative kernel, pipelined
  * chain, a single plugin -- jb_kernel_time_ms covers those).  Both synchronise the stream.  No counterpart in the
  * reference; measurement only (bench.py's per-kernel roofline). */
+/* The time slices jb_process_host cuts a render of `total_blocks` host blocks into when a slice holds `slice_blocks` of them
+ * (the last slices halve down to one block when `taper`): writes the first block of every slice, then total_blocks, into
+ * first[0 .. capacity) and returns the number of slices (or a negative jb_status).  Needs no device; for tests and tools. */
+int jb_plan_slices(int total_blocks, int slice_blocks, int taper, int* first, int capacity);
 int jb_enable_slot_timing(jb_engine* e, int on);
 int jb_slot_time_ms(jb_engine* e, int slot, double* ms, long long* launches);
 

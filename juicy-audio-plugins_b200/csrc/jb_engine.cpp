@@ -1421,6 +1421,35 @@ extern "C" int jbk_launch_float_to_pcm16(const float* src, int16_t* dst, long lo
 
 namespace {
 
+// Time slices of a host-buffer render (jb_process_host): `sliceBlocks` host blocks each, the last ones halving down to one
+// block when `taper` (nothing overlaps the final slice's render and download, so it should be short).  Returns the first
+// block of every slice, then totalBlocks.
+std::vector<int> planSlices(int totalBlocks, int sliceBlocks, bool taper)
+{
+    std::vector<int> first;
+    sliceBlocks = std::max(1, std::min(sliceBlocks, totalBlocks));
+    std::vector<int> tail;                       // 1, 2, 4, ... blocks, walked from the end of the call
+    if (taper && totalBlocks >= 4 * sliceBlocks)
+        for (int len = 1; len < sliceBlocks; len *= 2)
+            tail.push_back(len);
+    int tailBlocks = 0;
+    for (int len : tail)
+        tailBlocks += len;
+    int b = 0;
+    for (; b + sliceBlocks <= totalBlocks - tailBlocks; b += sliceBlocks)
+        first.push_back(b);
+    if (b < totalBlocks - tailBlocks) {          // ragged rest of the uniform part
+        first.push_back(b);
+        b = totalBlocks - tailBlocks;
+    }
+    for (size_t i = tail.size(); i-- > 0;) {
+        first.push_back(b);
+        b += tail[i];
+    }
+    first.push_back(totalBlocks);
+    return first;
+}
+
 // Does a render leave the audio as it is?  A chain of JuicyInfer instances whose trim is 0 dB everywhere: applyGain(1) is a
 // no-op (JuicyInfer/PluginProcessor.cpp:79), the plugin only scores.  (Pending automation: conservatively no.)
 bool audioUntouched(const jb_engine* e)
@@ -1508,28 +1537,7 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
     int sliceBlocks = (int) std::max({ (size_t) minSliceBlocks, rowBlocks, sliceTarget / std::max<size_t>(1, blockBytesAllClips) });
     sliceBlocks = std::min(sliceBlocks, totalBlocks);
     // slice s covers host blocks [sliceFirst[s], sliceFirst[s + 1])
-    std::vector<int> sliceFirst;
-    {
-        std::vector<int> tail;                       // 1, 2, 4, ... blocks, walked from the end of the call
-        if (taper && totalBlocks >= 4 * sliceBlocks)
-            for (int len = 1; len < sliceBlocks; len *= 2)
-                tail.push_back(len);
-        int tailBlocks = 0;
-        for (int len : tail)
-            tailBlocks += len;
-        int b = 0;
-        for (; b + sliceBlocks <= totalBlocks - tailBlocks; b += sliceBlocks)
-            sliceFirst.push_back(b);
-        if (b < totalBlocks - tailBlocks) {          // ragged rest of the uniform part
-            sliceFirst.push_back(b);
-            b = totalBlocks - tailBlocks;
-        }
-        for (size_t i = tail.size(); i-- > 0;) {
-            sliceFirst.push_back(b);
-            b += tail[i];
-        }
-        sliceFirst.push_back(totalBlocks);
-    }
+    const std::vector<int> sliceFirst = planSlices(totalBlocks, sliceBlocks, taper);
     const int nSlices = (int) sliceFirst.size() - 1;
 
     if (e->copyIn == nullptr) {
@@ -1696,6 +1704,17 @@ int processHost(jb_engine* e, const void* h_in_v, void* h_out_v, int n_samples, 
 } // namespace
 
 extern "C" {
+
+int jb_plan_slices(int total_blocks, int slice_blocks, int taper, int* first, int capacity)
+{
+    if (total_blocks <= 0 || slice_blocks <= 0)
+        return fail(JB_ERR_ARG, "jb_plan_slices: block counts must be positive");
+    const std::vector<int> plan = planSlices(total_blocks, slice_blocks, taper != 0);
+    if (first != nullptr)
+        for (int i = 0; i < capacity && i < (int) plan.size(); ++i)
+            first[i] = plan[(size_t) i];
+    return (int) plan.size() - 1;
+}
 
 int jb_process_host(jb_engine* e, const float* h_in, float* h_out, int n_samples)
 {

@@ -104,6 +104,7 @@ def lib():
         "jb_copy_to_device": (ci, [ci, vp, vp, ctypes.c_size_t]),
         "jb_copy_to_host": (ci, [ci, vp, vp, ctypes.c_size_t]),
         "jb_kernel_time_ms": (ci, [vp, ctypes.POINTER(cd), ctypes.POINTER(cll)]),
+        "jb_plan_slices": (ci, [ci, ci, ci, ctypes.POINTER(ci), ci]),
         "jb_enable_slot_timing": (ci, [vp, ci]),
         "jb_slot_time_ms": (ci, [vp, ci, ctypes.POINTER(cd), ctypes.POINTER(cll)]),
         "jb_set_path": (ci, [vp, ci]),
@@ -459,6 +460,16 @@ class BatchProcessor:
             _check(lib().jb_slot_time_ms(self._h, s, ctypes.byref(ms), ctypes.byref(n)))
             out.append((ms.value, n.value))
         return out
+
+
+def plan_slices(total_blocks, slice_blocks, taper=True):
+    """First host block of every time slice of a jb_process_host render, then total_blocks (jb_plan_slices; no device needed)."""
+    cap = int(total_blocks) + 2
+    buf = (ctypes.c_int * cap)()
+    n = lib().jb_plan_slices(int(total_blocks), int(slice_blocks), 1 if taper else 0, buf, cap)
+    if n < 0:
+        _check(n)
+    return list(buf[:n + 1])
 
 
 def shard_range(n_clips, rank, world):

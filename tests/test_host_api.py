@@ -127,3 +127,21 @@ def test_shard_range_partitions(jb):
         assert max(hi - lo for lo, hi in ranges) - min(hi - lo for lo, hi in ranges) <= 1
     with pytest.raises(jb.JuicyBatchError):
         jb.shard_range(10, 4, 4)
+
+
+def test_host_render_slice_plan(jb):
+    """jb_plan_slices (the time slices of jb_process_host; no device needed): every plan covers [0, total) exactly once in
+    order, uniform slices of the requested size, and -- tapered -- a tail that halves down to one block."""
+    for total in (1, 2, 3, 5, 12, 13, 94, 938):
+        for per in (1, 2, 3, 5, 6, 8, 94, 200):
+            for taper in (False, True):
+                plan = jb.plan_slices(total, per, taper)
+                assert plan[0] == 0 and plan[-1] == total
+                sizes = [b - a for a, b in zip(plan, plan[1:])]
+                assert all(s > 0 for s in sizes) and max(sizes) <= min(per, total)
+                if not taper or total < 4 * min(per, total):
+                    assert sizes[:-1] == [min(per, total)] * (len(sizes) - 1)      # only the last slice may be ragged
+    assert [b - a for a, b in zip(*(lambda p: (p, p[1:]))(jb.plan_slices(94, 6, True)))][-4:] == [3, 4, 2, 1]   # 66..84 uniform, ragged 3, then 4, 2, 1
+    assert jb.plan_slices(94, 1, True) == list(range(95))
+    with pytest.raises(jb.JuicyBatchError):
+        jb.plan_slices(0, 4)
